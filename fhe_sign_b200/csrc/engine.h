@@ -1,0 +1,49 @@
+// engine.h — the per-context device state behind fsc_ctx (one CUDA stream, keys, scratch).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "fsc_internal.h"
+
+namespace fsc {
+
+struct Luts {
+    size_t n = 0;
+    uint64_t* d = nullptr;      // [n][N] accumulator polynomials
+};
+
+void build_lut_poly(const fsc_params& p, const uint64_t* table, uint64_t* poly);
+
+struct Engine {
+    fsc_params p;
+    int dev = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void* bsk_f = nullptr;          // Fourier bootstrapping key [n][32 r][4 g][32 lane] complex f64
+    uint64_t* ksk = nullptr;        // [kN][l_ks][n+1]
+    uint64_t* scratch_small = nullptr;   // keyswitch outputs of the current batch
+    uint32_t* scratch_idx = nullptr;     // LUT indices of the current batch
+    size_t scratch_cap = 0;
+    uint64_t* scratch_big = nullptr;     // host-buffer entry point staging (in | out)
+    size_t scratch_big_cap = 0;
+    void* pinned = nullptr;
+    size_t pinned_cap = 0;
+    uint64_t launches = 0;
+
+    Engine(const fsc_params& prm, int device, uintptr_t ext_stream);
+    ~Engine();
+    Engine(const Engine&) = delete;
+    Engine& operator=(const Engine&) = delete;
+
+    void use();
+    void upload_keys(const uint64_t* bsk_std, size_t bsk_words, const uint64_t* ksk_h, size_t ksk_words);
+    void ensure_scratch(size_t count);
+    void ensure_pinned(size_t bytes);
+    const uint32_t* stage_lut_idx(const uint32_t* lut_idx, size_t count, const Luts* luts);
+    void keyswitch(const uint64_t* in_big, uint64_t* out_small, size_t count);
+    void pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut_idx_dev, uint64_t* out_big, size_t count);
+    void ks_pbs(const uint64_t* in_big, const Luts* luts, const uint32_t* lut_idx_dev, uint64_t* out_big, size_t count);
+};
+
+}  // namespace fsc

@@ -1,0 +1,479 @@
+// fsc_api.cu — context, device buffers and the C ABI of include/fhe_sign_cuda.h.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "fsc_internal.h"
+#include "engine.h"
+
+namespace fsc {
+
+static thread_local std::string g_create_error;
+
+// ---- LUT polynomial construction (integer host code; what tfhe's generate_lookup_table does) ----
+void build_lut_poly(const fsc_params& p, const uint64_t* table, uint64_t* poly) {
+    const uint32_t N = p.poly_size, space = p.message_modulus * p.carry_modulus, box = N / space, half = box / 2;
+    const uint64_t delta = ((uint64_t)1 << 63) / space;
+    std::vector<uint64_t> tmp(N);
+    for (uint32_t i = 0; i < space; ++i)
+        for (uint32_t j = 0; j < box; ++j) tmp[i * box + j] = table[i] * delta;
+    for (uint32_t j = 0; j < N; ++j) {
+        const uint32_t s = j + half;
+        poly[j] = s < N ? tmp[s] : (uint64_t)0 - tmp[s - N];
+    }
+}
+
+Engine::Engine(const fsc_params& prm, int device, uintptr_t ext_stream) : p(prm), dev(device) {
+    if (p.acc_bits == 0) p.acc_bits = 64;
+    if (p.glwe_dim != 1 || p.poly_size != 2048 || p.pbs_level != 1)
+        throw Error(FSC_ERR_PARAMS, "kernels are specialised for glwe_dim=1, poly_size=2048, pbs_level=1");
+    if (p.acc_bits != 64 && p.acc_bits != 32) throw Error(FSC_ERR_PARAMS, "acc_bits must be 32 or 64");
+    if (p.lwe_dim == 0 || p.lwe_dim > 4096 || p.pbs_base_log < 8 || p.pbs_base_log > 30)
+        throw Error(FSC_ERR_PARAMS, "lwe_dim / pbs_base_log out of range");
+    if (p.ks_level == 0 || p.ks_level > 8 || p.ks_base_log == 0 || p.ks_base_log > 7)
+        throw Error(FSC_ERR_PARAMS, "keyswitch decomposition out of range");
+    if (p.message_modulus * p.carry_modulus == 0 || (p.poly_size % (p.message_modulus * p.carry_modulus)) != 0)
+        throw Error(FSC_ERR_PARAMS, "message/carry modulus must divide poly_size");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw Error(FSC_ERR_CUDA, std::string("no CUDA device available (no CPU fallback exists): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) throw Error(FSC_ERR_BAD_ARG, "device index out of range");
+    FSC_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FSC_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) throw Error(FSC_ERR_CUDA, "this library is built for sm_100a (B200) only");
+    sm_count = prop.multiProcessorCount;
+    if (ext_stream) { stream = reinterpret_cast<cudaStream_t>(ext_stream); own_stream = false; }
+    else { FSC_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
+    FSC_CUDA_CHECK(cudaEventCreate(&ev0));
+    FSC_CUDA_CHECK(cudaEventCreate(&ev1));
+    pbs_init_constants();
+}
+
+Engine::~Engine() {
+    cudaSetDevice(dev);
+    cudaStreamSynchronize(stream);
+    if (bsk_f) cudaFree(bsk_f);
+    if (ksk) cudaFree(ksk);
+    if (scratch_small) cudaFree(scratch_small);
+    if (scratch_idx) cudaFree(scratch_idx);
+    if (scratch_big) cudaFree(scratch_big);
+    if (pinned) cudaFreeHost(pinned);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+}
+
+void Engine::use() { FSC_CUDA_CHECK(cudaSetDevice(dev)); }
+
+void Engine::upload_keys(const uint64_t* bsk_std, size_t bsk_words, const uint64_t* ksk_h, size_t ksk_words) {
+    use();
+    const size_t n = p.lwe_dim, N = p.poly_size;
+    const size_t want_bsk = n * 4 * N, want_ksk = (size_t)N * p.ks_level * (n + 1);
+    FSC_REQUIRE(bsk_std && ksk_h, "null key pointer");
+    FSC_REQUIRE(bsk_words == want_bsk, "bootstrapping key size does not match the parameter set");
+    FSC_REQUIRE(ksk_words == want_ksk, "keyswitching key size does not match the parameter set");
+    if (bsk_f) { cudaFree(bsk_f); bsk_f = nullptr; }
+    if (ksk) { cudaFree(ksk); ksk = nullptr; }
+    uint64_t* tmp = nullptr;
+    FSC_CUDA_CHECK(cudaMalloc(&tmp, want_bsk * 8));
+    cudaError_t e = cudaMalloc(&bsk_f, n * 32 * 4 * 32 * 16);
+    if (e != cudaSuccess) { cudaFree(tmp); FSC_CUDA_CHECK(e); }
+    e = cudaMalloc(&ksk, want_ksk * 8);
+    if (e != cudaSuccess) { cudaFree(tmp); FSC_CUDA_CHECK(e); }
+    FSC_CUDA_CHECK(cudaMemcpyAsync(tmp, bsk_std, want_bsk * 8, cudaMemcpyHostToDevice, stream));
+    FSC_CUDA_CHECK(cudaMemcpyAsync(ksk, ksk_h, want_ksk * 8, cudaMemcpyHostToDevice, stream));
+    launch_bsk_convert(tmp, bsk_f, (int)n, stream); ++launches;
+    FSC_CUDA_CHECK(cudaGetLastError());
+    FSC_CUDA_CHECK(cudaStreamSynchronize(stream));
+    cudaFree(tmp);
+}
+
+void Engine::ensure_scratch(size_t count) {
+    if (count <= scratch_cap) return;
+    use();
+    FSC_CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (scratch_small) cudaFree(scratch_small);
+    if (scratch_idx) cudaFree(scratch_idx);
+    scratch_small = nullptr; scratch_idx = nullptr; scratch_cap = 0;
+    size_t cap = 1024;
+    while (cap < count) cap *= 2;
+    FSC_CUDA_CHECK(cudaMalloc(&scratch_small, cap * (p.lwe_dim + 1) * 8));
+    FSC_CUDA_CHECK(cudaMalloc(&scratch_idx, cap * sizeof(uint32_t)));
+    scratch_cap = cap;
+}
+
+void Engine::ensure_pinned(size_t bytes) {
+    if (bytes <= pinned_cap) return;
+    use();
+    FSC_CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (pinned) cudaFreeHost(pinned);
+    pinned = nullptr; pinned_cap = 0;
+    size_t cap = 1 << 16;
+    while (cap < bytes) cap *= 2;
+    FSC_CUDA_CHECK(cudaMallocHost(&pinned, cap));
+    pinned_cap = cap;
+}
+
+const uint32_t* Engine::stage_lut_idx(const uint32_t* lut_idx, size_t count, const Luts* luts) {
+    if (!lut_idx) return nullptr;
+    for (size_t i = 0; i < count; ++i) FSC_REQUIRE(lut_idx[i] < luts->n, "lut index out of range");
+    ensure_scratch(count);
+    // the pinned staging area is reused by the next call: wait for earlier copies out of it first
+    FSC_CUDA_CHECK(cudaStreamSynchronize(stream));
+    ensure_pinned(count * sizeof(uint32_t));
+    memcpy(pinned, lut_idx, count * sizeof(uint32_t));
+    FSC_CUDA_CHECK(cudaMemcpyAsync(scratch_idx, pinned, count * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    return scratch_idx;
+}
+
+void Engine::keyswitch(const uint64_t* in_big, uint64_t* out_small, size_t count) {
+    use();
+    if (!ksk) throw Error(FSC_ERR_NO_KEYS, "server keys not uploaded");
+    launch_keyswitch(ksk, in_big, out_small, (int)count, (int)p.poly_size, (int)p.lwe_dim, (int)p.ks_base_log,
+                     (int)p.ks_level, stream);
+    ++launches;
+    FSC_CUDA_CHECK(cudaGetLastError());
+}
+
+void Engine::pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut_idx_dev, uint64_t* out_big, size_t count) {
+    use();
+    if (!bsk_f) throw Error(FSC_ERR_NO_KEYS, "server keys not uploaded");
+    launch_pbs((int)p.acc_bits, bsk_f, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, out_big,
+               (int)count, stream);
+    ++launches;
+    FSC_CUDA_CHECK(cudaGetLastError());
+}
+
+void Engine::ks_pbs(const uint64_t* in_big, const Luts* luts, const uint32_t* lut_idx_dev, uint64_t* out_big, size_t count) {
+    ensure_scratch(count);
+    keyswitch(in_big, scratch_small, count);
+    pbs(scratch_small, luts, lut_idx_dev, out_big, count);
+}
+
+}  // namespace fsc
+
+// =======================================================================================
+// C ABI
+// =======================================================================================
+using fsc::Engine;
+using fsc::Error;
+
+struct fsc_ctx {
+    Engine* eng = nullptr;
+    std::string err;
+};
+struct fsc_lwe {
+    uint32_t kind;
+    size_t count, words;
+    uint64_t* d;
+};
+struct fsc_luts : fsc::Luts {};
+
+#define FSC_API_BEGIN(ctx)                                   \
+    if (!(ctx)) return FSC_ERR_BAD_ARG;                      \
+    try {
+#define FSC_API_END(ctx)                                     \
+    }                                                        \
+    catch (const Error& e) { (ctx)->err = e.what(); return e.code; }                     \
+    catch (const std::bad_alloc&) { (ctx)->err = "host allocation failed"; return FSC_ERR_OOM; } \
+    catch (const std::exception& e) { (ctx)->err = e.what(); return FSC_ERR_INTERNAL; }   \
+    catch (...) { (ctx)->err = "unknown error"; return FSC_ERR_INTERNAL; }               \
+    return FSC_OK;
+
+extern "C" {
+
+fsc_status fsc_ctx_create(const fsc_params* params, int32_t device, uintptr_t stream, fsc_ctx** out) {
+    if (!params || !out) { fsc::g_create_error = "null argument"; return FSC_ERR_BAD_ARG; }
+    *out = nullptr;
+    fsc_ctx* c = nullptr;
+    try {
+        c = new fsc_ctx();
+        c->eng = new Engine(*params, device, stream);
+        *out = c;
+        return FSC_OK;
+    } catch (const Error& e) {
+        fsc::g_create_error = e.what(); delete c; return e.code;
+    } catch (const std::exception& e) {
+        fsc::g_create_error = e.what(); delete c; return FSC_ERR_INTERNAL;
+    } catch (...) {
+        fsc::g_create_error = "unknown error"; delete c; return FSC_ERR_INTERNAL;
+    }
+}
+
+fsc_status fsc_ctx_destroy(fsc_ctx* ctx) {
+    if (!ctx) return FSC_ERR_BAD_ARG;
+    try { delete ctx->eng; } catch (...) {}
+    delete ctx;
+    return FSC_OK;
+}
+
+const char* fsc_last_error(const fsc_ctx* ctx) { return ctx ? ctx->err.c_str() : fsc::g_create_error.c_str(); }
+
+fsc_status fsc_get_params(const fsc_ctx* ctx, fsc_params* out) {
+    if (!ctx || !out) return FSC_ERR_BAD_ARG;
+    *out = ctx->eng->p;
+    return FSC_OK;
+}
+
+fsc_status fsc_sync(fsc_ctx* ctx) {
+    FSC_API_BEGIN(ctx)
+    ctx->eng->use();
+    FSC_CUDA_CHECK(cudaStreamSynchronize(ctx->eng->stream));
+    FSC_API_END(ctx)
+}
+
+fsc_status fsc_keys_upload(fsc_ctx* ctx, const uint64_t* bsk_std, size_t bsk_words, const uint64_t* ksk, size_t ksk_words) {
+    FSC_API_BEGIN(ctx)
+    ctx->eng->upload_keys(bsk_std, bsk_words, ksk, ksk_words);
+    FSC_API_END(ctx)
+}
+
+fsc_status fsc_lwe_alloc(fsc_ctx* ctx, uint32_t kind, size_t count, fsc_lwe** out) {
+    FSC_API_BEGIN(ctx)
+    FSC_REQUIRE(out, "null out pointer");
+    *out = nullptr;
+    FSC_REQUIRE(kind == FSC_LWE_BIG || kind == FSC_LWE_SMALL, "unknown ciphertext kind");
+    ctx->eng->use();
+    fsc_lwe* a = new fsc_lwe();
+    a->kind = kind; a->count = count;
+    a->words = kind == FSC_LWE_BIG ? (size_t)ctx->eng->p.glwe_dim * ctx->eng->p.poly_size + 1 : (size_t)ctx->eng->p.lwe_dim + 1;
+    a->d = nullptr;
+    if (count) {
+        cudaError_t e = cudaMalloc(&a->d, count * a->words * 8);
+        if (e != cudaSuccess) { delete a; FSC_CUDA_CHECK(e); }
+    }
+    *out = a;
+    FSC_API_END(ctx)
+}
+
+fsc_status fsc_lwe_free(fsc_ctx* ctx, fsc_lwe* a) {
+    FSC_API_BEGIN(ctx)
+    if (a) {
+        ctx->eng->use();
+        FSC_CUDA_CHECK(cudaStreamSynchronize(ctx->eng->stream));
+        if (a->d) cudaFree(a->d);
+        delete a;
+    }
+    FSC_API_END(ctx)
+}
+
+fsc_status fsc_lwe_upload(fsc_ctx* ctx, fsc_lwe* dst, size_t first, const uint64_t* host, size_t count) {
+    FSC_API_BEGIN(ctx)
+    FSC_REQUIRE(dst && (host || !count), "null argument");
+    FSC_REQUIRE(first <= dst->count && count <= dst->count - first, "range exceeds the ciphertext array");
+    ctx->eng->use();
+    if (count) {
+        FSC_CUDA_CHECK(cudaMemcpyAsync(dst->d + first * dst->words, host, count * dst->words * 8, cudaMemcpyHostToDevice, ctx->eng->stream));
+        FSC_CUDA_CHECK(cudaStreamSynchronize(ctx->eng->stream));
+    }
+    FSC_API_END(ctx)
+}
+
+fsc_status fsc_lwe_download(fsc_ctx* ctx, const fsc_lwe* src, size_t first, uint64_t* host, size_t count) {
+    FSC_API_BEGIN(ctx)
+    FSC_REQUIRE(src && (host || !count), "null argument");
+    FSC_REQUIRE(first <= src->count && count <= src->count - first, "range exceeds the ciphertext array");
+    ctx->eng->use();
+    if (count)
+        FSC_CUDA_CHECK(cudaMemcpyAsync(host, src->d + first * src->words, count * src->words * 8, cudaMemcpyDeviceToHost, ctx->eng->stream));
+    FSC_CUDA_CHECK(cudaStreamSynchronize(ctx->eng->stream));
+    FSC_API_END(ctx)
+}
+
+fsc_status fsc_lwe_info(const fsc_lwe* a, uint32_t* kind, size_t* count, size_t* words, void** device_ptr) {
+    if (!a) return FSC_ERR_BAD_ARG;
+    if (kind) *kind = a->kind;
+    if (count) *count = a->count;
+    if (words) *words = a->words;
+    if (device_ptr) *device_ptr = a->d;
+    return FSC_OK;
+}
+
+static fsc_status luts_upload_impl(fsc_ctx* ctx, const uint64_t* polys, size_t n_luts, fsc_luts** out) {
+    FSC_API_BEGIN(ctx)
+    FSC_REQUIRE(polys && out && n_luts, "null argument or zero LUTs");
+    *out = nullptr;
+    ctx->eng->use();
+    fsc_luts* l = new fsc_luts();
+    l->n = n_luts; l->d = nullptr;
+    const size_t bytes = n_luts * ctx->eng->p.poly_size * 8;
+    cudaError_t e = cudaMalloc(&l->d, bytes);
+    if (e != cudaSuccess) { delete l; FSC_CUDA_CHECK(e); }
+    e = cudaMemcpyAsync(l->d, polys, bytes, cudaMemcpyHostToDevice, ctx->eng->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->eng->stream);
+    if (e != cudaSuccess) { cudaFree(l->d); delete l; FSC_CUDA_CHECK(e); }
+    *out = l;
+    FSC_API_END(ctx)
+}
+
+fsc_status fsc_luts_upload(fsc_ctx* ctx, const uint64_t* polys, size_t n_luts, fsc_luts** out) {
+    return luts_upload_impl(ctx, polys, n_luts, out);
+}
+
+fsc_status fsc_luts_from_tables(fsc_ctx* ctx, const uint64_t* tables, size_t n_luts, fsc_luts** out) {
+    if (!ctx) return FSC_ERR_BAD_ARG;
+    if (!tables || !out || !n_luts) { ctx->err = "null argument or zero LUTs"; return FSC_ERR_BAD_ARG; }
+    std::vector<uint64_t> polys;
+    try {
+        const fsc_params& p = ctx->eng->p;
+        const size_t space = p.message_modulus * p.carry_modulus;
+        polys.resize(n_luts * p.poly_size);
+        for (size_t i = 0; i < n_luts; ++i) fsc::build_lut_poly(p, tables + i * space, polys.data() + i * p.poly_size);
+    } catch (...) { ctx->err = "host allocation failed"; return FSC_ERR_OOM; }
+    return luts_upload_impl(ctx, polys.data(), n_luts, out);
+}
+
+fsc_status fsc_luts_free(fsc_ctx* ctx, fsc_luts* l) {
+    FSC_API_BEGIN(ctx)
+    if (l) {
+        ctx->eng->use();
+        FSC_CUDA_CHECK(cudaStreamSynchronize(ctx->eng->stream));
+        if (l->d) cudaFree(l->d);
+        delete l;
+    }
+    FSC_API_END(ctx)
+}
+
+static void check_range(const fsc_lwe* a, uint32_t kind, size_t first, size_t count, const char* what) {
+    if (!a) throw Error(FSC_ERR_BAD_ARG, std::string(what) + ": null ciphertext array");
+    if (a->kind != kind) throw Error(FSC_ERR_BAD_ARG, std::string(what) + ": wrong ciphertext kind");
+    if (first > a->count || count > a->count - first) throw Error(FSC_ERR_BAD_ARG, std::string(what) + ": range exceeds the ciphertext array");
+}
+
+fsc_status fsc_keyswitch_batch(fsc_ctx* ctx, const fsc_lwe* in_big, size_t in_first, fsc_lwe* out_small, size_t out_first, size_t count) {
+    FSC_API_BEGIN(ctx)
+    check_range(in_big, FSC_LWE_BIG, in_first, count, "keyswitch input");
+    check_range(out_small, FSC_LWE_SMALL, out_first, count, "keyswitch output");
+    if (count) ctx->eng->keyswitch(in_big->d + in_first * in_big->words, out_small->d + out_first * out_small->words, count);
+    FSC_API_END(ctx)
+}
+
+fsc_status fsc_pbs_batch(fsc_ctx* ctx, const fsc_lwe* in_small, size_t in_first, const fsc_luts* luts, const uint32_t* lut_idx,
+                         fsc_lwe* out_big, size_t out_first, size_t count) {
+    FSC_API_BEGIN(ctx)
+    FSC_REQUIRE(luts, "null LUT handle");
+    check_range(in_small, FSC_LWE_SMALL, in_first, count, "pbs input");
+    check_range(out_big, FSC_LWE_BIG, out_first, count, "pbs output");
+    if (count) {
+        const uint32_t* di = ctx->eng->stage_lut_idx(lut_idx, count, luts);
+        ctx->eng->pbs(in_small->d + in_first * in_small->words, luts, di, out_big->d + out_first * out_big->words, count);
+    }
+    FSC_API_END(ctx)
+}
+
+fsc_status fsc_ks_pbs_batch(fsc_ctx* ctx, const fsc_lwe* in_big, size_t in_first, const fsc_luts* luts, const uint32_t* lut_idx,
+                            fsc_lwe* out_big, size_t out_first, size_t count) {
+    FSC_API_BEGIN(ctx)
+    FSC_REQUIRE(luts, "null LUT handle");
+    check_range(in_big, FSC_LWE_BIG, in_first, count, "ks_pbs input");
+    check_range(out_big, FSC_LWE_BIG, out_first, count, "ks_pbs output");
+    if (count) {
+        const uint32_t* di = ctx->eng->stage_lut_idx(lut_idx, count, luts);
+        ctx->eng->ks_pbs(in_big->d + in_first * in_big->words, luts, di, out_big->d + out_first * out_big->words, count);
+    }
+    FSC_API_END(ctx)
+}
+
+fsc_status fsc_apply_lut_host(fsc_ctx* ctx, const uint64_t* in_host, const fsc_luts* luts, const uint32_t* lut_idx,
+                              uint64_t* out_host, size_t count) {
+    FSC_API_BEGIN(ctx)
+    FSC_REQUIRE(luts && (in_host || !count) && (out_host || !count), "null argument");
+    if (count) {
+        Engine* e = ctx->eng;
+        e->use();
+        const size_t words = (size_t)e->p.glwe_dim * e->p.poly_size + 1;
+        if (count > e->scratch_big_cap) {
+            FSC_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+            if (e->scratch_big) cudaFree(e->scratch_big);
+            e->scratch_big = nullptr; e->scratch_big_cap = 0;
+            FSC_CUDA_CHECK(cudaMalloc(&e->scratch_big, 2 * count * words * 8));
+            e->scratch_big_cap = count;
+        }
+        uint64_t* din = e->scratch_big;
+        uint64_t* dout = e->scratch_big + e->scratch_big_cap * words;
+        const uint32_t* di = e->stage_lut_idx(lut_idx, count, luts);
+        FSC_CUDA_CHECK(cudaMemcpyAsync(din, in_host, count * words * 8, cudaMemcpyHostToDevice, e->stream));
+        e->ks_pbs(din, luts, di, dout, count);
+        FSC_CUDA_CHECK(cudaMemcpyAsync(out_host, dout, count * words * 8, cudaMemcpyDeviceToHost, e->stream));
+        FSC_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    }
+    FSC_API_END(ctx)
+}
+
+fsc_status fsc_timer_start(fsc_ctx* ctx) {
+    FSC_API_BEGIN(ctx)
+    ctx->eng->use();
+    FSC_CUDA_CHECK(cudaEventRecord(ctx->eng->ev0, ctx->eng->stream));
+    FSC_API_END(ctx)
+}
+
+fsc_status fsc_timer_stop(fsc_ctx* ctx, float* ms) {
+    FSC_API_BEGIN(ctx)
+    FSC_REQUIRE(ms, "null argument");
+    ctx->eng->use();
+    FSC_CUDA_CHECK(cudaEventRecord(ctx->eng->ev1, ctx->eng->stream));
+    FSC_CUDA_CHECK(cudaEventSynchronize(ctx->eng->ev1));
+    FSC_CUDA_CHECK(cudaEventElapsedTime(ms, ctx->eng->ev0, ctx->eng->ev1));
+    FSC_API_END(ctx)
+}
+
+fsc_status fsc_launch_count(const fsc_ctx* ctx, uint64_t* out) {
+    if (!ctx || !out) return FSC_ERR_BAD_ARG;
+    *out = ctx->eng->launches;
+    return FSC_OK;
+}
+
+fsc_status fsc_measure_fp64_peak(fsc_ctx* ctx, double* tflops) {
+    FSC_API_BEGIN(ctx)
+    FSC_REQUIRE(tflops, "null argument");
+    Engine* e = ctx->eng;
+    e->use();
+    double* sink = nullptr;
+    FSC_CUDA_CHECK(cudaMalloc(&sink, 8));
+    float best = 1e30f;
+    double fmas = 0;
+    cudaError_t err = cudaSuccess;
+    for (int rep = 0; rep < 4 && err == cudaSuccess; ++rep) {          // first repetition warms up
+        err = cudaEventRecord(e->ev0, e->stream);
+        fmas = fsc::launch_fp64_peak(sink, e->sm_count, 4096, e->stream); ++e->launches;
+        if (err == cudaSuccess) err = cudaGetLastError();
+        if (err == cudaSuccess) err = cudaEventRecord(e->ev1, e->stream);
+        if (err == cudaSuccess) err = cudaEventSynchronize(e->ev1);
+        float ms = 0;
+        if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaFree(sink);
+    FSC_CUDA_CHECK(err);
+    *tflops = 2.0 * fmas / (best * 1e-3) / 1e12;
+    FSC_API_END(ctx)
+}
+
+fsc_status fsc_debug_negacyclic_mul(fsc_ctx* ctx, const uint64_t* a, const int64_t* b, uint64_t* c, size_t count) {
+    FSC_API_BEGIN(ctx)
+    FSC_REQUIRE(a && b && c && count, "null argument");
+    Engine* e = ctx->eng;
+    e->use();
+    const size_t bytes = count * e->p.poly_size * 8;
+    uint64_t* d = nullptr;
+    FSC_CUDA_CHECK(cudaMalloc(&d, 3 * bytes));
+    cudaError_t err = cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, e->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d + bytes / 8, b, bytes, cudaMemcpyHostToDevice, e->stream);
+    if (err == cudaSuccess) {
+        fsc::launch_negacyclic_mul(d, reinterpret_cast<const int64_t*>(d + bytes / 8), d + 2 * (bytes / 8), (int)count, e->stream);
+        ++e->launches;
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaMemcpyAsync(c, d + 2 * (bytes / 8), bytes, cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cudaFree(d);
+    FSC_CUDA_CHECK(err);
+    FSC_API_END(ctx)
+}
+
+}  // extern "C"

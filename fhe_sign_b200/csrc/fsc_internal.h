@@ -1,0 +1,43 @@
+// fsc_internal.h — declarations shared by the kernels and the C-ABI layer (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/fhe_sign_cuda.h"
+
+namespace fsc {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define FSC_CUDA_CHECK(expr)                                                                          \
+    do {                                                                                              \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            throw ::fsc::Error(e__ == cudaErrorMemoryAllocation ? FSC_ERR_OOM : FSC_ERR_CUDA,         \
+                               std::string(#expr) + ": " + cudaGetErrorString(e__));                  \
+    } while (0)
+
+#define FSC_REQUIRE(cond, msg)                                          \
+    do {                                                                \
+        if (!(cond)) throw ::fsc::Error(FSC_ERR_BAD_ARG, (msg));        \
+    } while (0)
+
+// pbs_kernel.cu
+void pbs_init_constants();
+void launch_bsk_convert(const uint64_t* bsk_std, void* bsk_fourier, int n, cudaStream_t st);
+void launch_pbs(int acc_bits, const void* bsk_fourier, const uint64_t* in_small, int n, int base_log,
+                const uint64_t* luts, const uint32_t* lut_idx, uint64_t* out_big, int count, cudaStream_t st);
+void launch_negacyclic_mul(const uint64_t* a, const int64_t* b, uint64_t* c, int count, cudaStream_t st);
+
+double launch_fp64_peak(double* sink, int sm_count, int iters, cudaStream_t st);
+
+// ks_kernel.cu
+void launch_keyswitch(const uint64_t* ksk, const uint64_t* in_big, uint64_t* out_small, int count, int big_dim,
+                      int n, int base_log, int level, cudaStream_t st);
+
+}  // namespace fsc

@@ -1,0 +1,253 @@
+// pbs_kernel.cu — batched programmable bootstrapping for sm_100a (k = 1, N = 2048, l = 1).
+//
+// Kernels:
+//   bsk_convert_kernel   standard-domain bootstrapping key -> Fourier domain, in the exact
+//                        (register position, lane) order the blind rotation consumes
+//   pbs_pair_kernel      two warps per ciphertext (one per GLWE polynomial): modulus switch,
+//                        accumulator init from the LUT, n CMUX steps (pbs_core.cuh), sample
+//                        extraction of coefficient 0
+//   negacyclic_mul_kernel / fft_roundtrip hooks for the parity tests
+//
+// Replaces (concept): tfhe 0.10.0 programmable_bootstrap_lwe_ciphertext (Cargo.lock:482-485), the
+// PBS half of shortint apply_lookup_table behind every operator in src/biguint.rs:110-248.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pbs_core.cuh"
+#include "fsc_internal.h"
+
+namespace fsc {
+
+__constant__ cplx c_s1[16];     // uniform pass-1 node constants (g = 32)
+
+struct S1Dev {
+    __device__ __forceinline__ cplx get(int ci) const { return c_s1[ci]; }
+};
+
+void pbs_init_constants() {
+    cplx h[16];
+    lane_consts(32, h);
+    FSC_CUDA_CHECK(cudaMemcpyToSymbol(c_s1, h, sizeof(h)));
+}
+
+// forward negacyclic FFT of the 32 x 32 complex points held by the warp (v[j2] at lane j1)
+__device__ __forceinline__ void warp_fft_fwd(int lane, cplx* xbuf, const cplx (&s2)[16], cplx (&v)[32]) {
+    dft32_fwd(v, S1Dev());
+    xpose_store_fwd(lane, xbuf, v);
+    __syncwarp();
+    xpose_load_fwd(lane, xbuf, v);
+    __syncwarp();
+    dft32_fwd(v, RegConsts(s2));
+}
+__device__ __forceinline__ void warp_fft_inv(int lane, cplx* xbuf, const cplx (&s2)[16], cplx (&v)[32]) {
+    dft32_inv(v, RegConsts(s2));
+    xpose_store_inv(lane, xbuf, v);
+    __syncwarp();
+    xpose_load_inv(lane, xbuf, v);
+    __syncwarp();
+    dft32_inv(v, S1Dev());
+}
+
+__device__ __forceinline__ cplx ldg_cplx(const cplx* p) {
+    const double2 d = __ldg(reinterpret_cast<const double2*>(p));
+    cplx r; r.x = d.x; r.y = d.y;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// Bootstrapping key conversion.  grid = n * 4 polynomials, block = 32.
+// in : bsk [n][p][l=1][q][2048] u64 (standard domain)      out: [n][r][g = 2p+q][lane] cplx
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) bsk_convert_kernel(const uint64_t* __restrict__ bsk, cplx* __restrict__ out) {
+    __shared__ cplx xbuf[1024];
+    const int lane = threadIdx.x;
+    const int i = blockIdx.x >> 2, g = blockIdx.x & 3;
+    const uint64_t* src = bsk + (size_t)blockIdx.x * kN;
+    cplx s2[16];
+    lane_consts(4 * lane + 1, s2);
+    cplx v[32];
+#pragma unroll
+    for (int j2 = 0; j2 < 32; ++j2) {
+        v[j2].x = (double)(int64_t)src[lane + 32 * j2];
+        v[j2].y = (double)(int64_t)src[lane + 32 * j2 + 1024];
+    }
+    warp_fft_fwd(lane, xbuf, s2, v);
+#pragma unroll
+    for (int r = 0; r < 32; ++r) out[(((size_t)i * 32 + r) * 4 + g) * 32 + lane] = v[r];
+}
+
+// ---------------------------------------------------------------------------------------
+// Blind rotation + sample extraction.  One CTA of two warps per ciphertext: warp p owns polynomial p
+// of the GLWE accumulator (p = 0 mask, p = 1 body) for the whole rotation.
+// shared memory: acc [2][1024] pair_t<AccT>  |  xbuf [2][1024] cplx (FFT transpose + MAC exchange)
+// Per CMUX step the two warps meet twice: once to swap their Fourier-domain digit polynomials
+// (every output polynomial needs both inputs) and once before the exchange buffer is reused.
+// ---------------------------------------------------------------------------------------
+constexpr int kGDepth = 4;      // register prefetch depth (frequency slots) of the GGSW stream
+
+template <typename AccT>
+__global__ void __launch_bounds__(64, 4) pbs_pair_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
+                                                       int n, int base_log, const uint64_t* __restrict__ luts,
+                                                       const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
+                                                       int count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int p = threadIdx.x >> 5;
+    pair_t<AccT>* acc_all = reinterpret_cast<pair_t<AccT>*>(smem_raw);
+    cplx* xbuf_all = reinterpret_cast<cplx*>(smem_raw + 2 * 1024 * sizeof(pair_t<AccT>));
+    pair_t<AccT>* acc = acc_all + p * 1024;
+    cplx* xbuf = xbuf_all + p * 1024;
+    const cplx* xother = xbuf_all + (1 - p) * 1024;
+    const int c = blockIdx.x;
+    if (c >= count) return;
+    const uint64_t* ct = in_small + (size_t)c * (n + 1);
+    const uint64_t* lut = luts + (size_t)(lut_idx ? lut_idx[c] : 0) * kN;
+
+    cplx s2[16];
+    lane_consts(4 * lane + 1, s2);
+
+    // accumulator <- (0, X^{-b} * LUT)
+    {
+        const int b = modswitch(ct[n]);
+#pragma unroll 4
+        for (int j2 = 0; j2 < 32; ++j2) {
+            const int idx = lane + 32 * j2;
+            pair_t<AccT> z; z.x = 0; z.y = 0;
+            acc[idx] = p ? lut_pair<AccT>(lut, idx, b) : z;
+        }
+    }
+    __syncwarp();
+
+    // GGSW stream of this warp: G[0][p] (g = p) and G[1][p] (g = 2 + p)
+    const cplx* gbase = bsk_f + lane + p * 32;
+    int a_chunk = 0;
+    for (int i = 0; i < n; ++i) {
+        if ((i & 31) == 0) a_chunk = (i + lane < n) ? modswitch(ct[i + lane]) : 0;
+        const int a = __shfl_sync(0xffffffffu, a_chunk, i & 31);
+        if (a == 0) continue;      // uniform across the CTA: both warps read the same ciphertext
+
+        const cplx* g = gbase + (size_t)i * (32 * 4 * 32);
+        cplx ga[kGDepth], gb[kGDepth];
+#pragma unroll
+        for (int r = 0; r < kGDepth; ++r) { ga[r] = ldg_cplx(g + (r * 4) * 32); gb[r] = ldg_cplx(g + (r * 4 + 2) * 32); }
+
+        cplx X[32];
+        cmux_head<AccT>(lane, acc, a, base_log, X);
+        warp_fft_fwd(lane, xbuf, s2, X);
+#pragma unroll
+        for (int r = 0; r < 32; ++r) xbuf[r * 32 + lane] = X[r];
+        __syncthreads();
+
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const cplx o = xother[r * 32 + lane];
+            const cplx g0 = ga[r % kGDepth], g1 = gb[r % kGDepth];      // G[0][p], G[1][p] at this slot
+            if (r + kGDepth < 32) {
+                ga[r % kGDepth] = ldg_cplx(g + ((r + kGDepth) * 4) * 32);
+                gb[r % kGDepth] = ldg_cplx(g + ((r + kGDepth) * 4 + 2) * 32);
+            }
+            const cplx x0 = p ? o : X[r];
+            const cplx x1 = p ? X[r] : o;
+            X[r].x = x0.x * g0.x - x0.y * g0.y + x1.x * g1.x - x1.y * g1.y;
+            X[r].y = x0.x * g0.y + x0.y * g0.x + x1.x * g1.y + x1.y * g1.x;
+        }
+        __syncthreads();
+
+        warp_fft_inv(lane, xbuf, s2, X);
+        cmux_tail<AccT>(lane, acc, X);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    uint64_t* out = out_big + (size_t)c * (kN + 1);
+    for (int j = threadIdx.x; j <= kN; j += 64) out[j] = extract_word<AccT>(acc_all, acc_all + 1024, j);
+}
+
+// ---------------------------------------------------------------------------------------
+// Test hook: c = a (torus) * b (small integers), negacyclic, through the kernel's own FFT.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) negacyclic_mul_kernel(const uint64_t* __restrict__ a, const int64_t* __restrict__ b,
+                                                             uint64_t* __restrict__ c) {
+    __shared__ cplx xbuf[1024];
+    const int lane = threadIdx.x;
+    a += (size_t)blockIdx.x * kN; b += (size_t)blockIdx.x * kN; c += (size_t)blockIdx.x * kN;
+    cplx s2[16];
+    lane_consts(4 * lane + 1, s2);
+    cplx va[32], vb[32];
+#pragma unroll
+    for (int j2 = 0; j2 < 32; ++j2) {
+        va[j2].x = (double)(int64_t)a[lane + 32 * j2]; va[j2].y = (double)(int64_t)a[lane + 32 * j2 + 1024];
+        vb[j2].x = (double)b[lane + 32 * j2];          vb[j2].y = (double)b[lane + 32 * j2 + 1024];
+    }
+    warp_fft_fwd(lane, xbuf, s2, va);
+    __syncwarp();
+    warp_fft_fwd(lane, xbuf, s2, vb);
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        const cplx x = va[r], y = vb[r];
+        va[r].x = x.x * y.x - x.y * y.y; va[r].y = x.x * y.y + x.y * y.x;
+    }
+    __syncwarp();
+    warp_fft_inv(lane, xbuf, s2, va);
+#pragma unroll
+    for (int j2 = 0; j2 < 32; ++j2) {
+        c[lane + 32 * j2] = to_acc<uint64_t>(va[j2].x);
+        c[lane + 32 * j2 + 1024] = to_acc<uint64_t>(va[j2].y);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------
+void launch_bsk_convert(const uint64_t* bsk, void* out, int n, cudaStream_t st) {
+    bsk_convert_kernel<<<n * 4, 32, 0, st>>>(bsk, reinterpret_cast<cplx*>(out));
+}
+
+template <typename AccT>
+static void launch_pbs_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
+                         const uint32_t* lut_idx, uint64_t* out_big, int count, cudaStream_t st) {
+    const size_t smem = 2 * 1024 * sizeof(pair_t<AccT>) + 2 * 1024 * sizeof(cplx);
+    static bool configured = false;
+    if (!configured) {
+        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_pair_kernel<AccT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    pbs_pair_kernel<AccT><<<count, 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts,
+                                                    lut_idx, out_big, count);
+}
+
+void launch_pbs(int acc_bits, const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
+                const uint32_t* lut_idx, uint64_t* out_big, int count, cudaStream_t st) {
+    if (count <= 0) return;
+    if (acc_bits == 32) launch_pbs_t<uint32_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, count, st);
+    else launch_pbs_t<uint64_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, count, st);
+}
+
+// ---------------------------------------------------------------------------------------
+// FP64 FMA peak probe (the roofline denominator north_star asks for; MEASURED_PEAKS.json has no FP64
+// figure).  8 independent FMA chains per thread, 4 CTAs x 256 threads per SM.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 12345.678) sink[0] = s;      // never true; keeps the chains alive
+}
+
+// returns the number of FMAs executed
+double launch_fp64_peak(double* sink, int sm_count, int iters, cudaStream_t st) {
+    const int blocks = sm_count * 4;
+    fp64_peak_kernel<<<blocks, 256, 0, st>>>(sink, iters, 0.999999, 1e-9);
+    return (double)blocks * 256.0 * (double)iters * 64.0;
+}
+
+void launch_negacyclic_mul(const uint64_t* a, const int64_t* b, uint64_t* c, int count, cudaStream_t st) {
+    negacyclic_mul_kernel<<<count, 32, 0, st>>>(a, b, c);
+}
+
+}  // namespace fsc

@@ -1,0 +1,128 @@
+/*
+ * fhe_sign_cuda.h — C ABI of libfhe_sign_cuda.so, the B200 (sm_100a) server-side engine that
+ * replaces the tfhe-rs CPU server key behind fhe-sign's BigUintFHE.
+ *
+ * Drop-in seam.  The reference installs a thread-local CPU server key with
+ * `tfhe::set_server_key(server_keys)` (src/biguint.rs:278, src/schnorr.rs:472, src/perf_test.rs:24)
+ * and every `FheUint32/FheUint64` operator (src/biguint.rs:110,116,135-143,221-248;
+ * src/perf_test.rs:28-54) then runs keyswitch + programmable bootstrap on the CPU.  The reference has
+ * no FFI of its own; these entry points are what a `fhe-sign-cuda` Rust crate binds with
+ * `extern "C"` so that biguint.rs keeps its API.
+ *
+ * Conventions
+ *  - every function returns an fsc_status (0 = OK); no C++ exception crosses this boundary;
+ *    fsc_last_error() gives the message of the last failure on that context (or of the last failed
+ *    fsc_ctx_create when ctx == NULL);
+ *  - handles are opaque and owned by the library; host buffers passed in are read or written during
+ *    the call only and are never freed by the library;
+ *  - a context is not thread-safe (it mirrors the thread-local set_server_key): one per host thread;
+ *    work is enqueued on the context's CUDA stream, in call order; fsc_sync() or any download waits;
+ *  - ciphertexts are LWE vectors of u64 words, mask first, body last: "big" = k*N+1 = 2049 words
+ *    (the radix blocks the reference's FheUint types are made of), "small" = n+1 words;
+ *  - there is no CPU fallback: if no usable CUDA device exists fsc_ctx_create fails with FSC_ERR_CUDA.
+ */
+#ifndef FHE_SIGN_CUDA_H
+#define FHE_SIGN_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t fsc_status;
+enum {
+    FSC_OK = 0,
+    FSC_ERR_BAD_ARG = 1,     /* null pointer, size mismatch, out-of-range index                 */
+    FSC_ERR_PARAMS = 2,      /* parameter set not supported by the kernels (k=1, N=2048, l=1)   */
+    FSC_ERR_OOM = 3,         /* device or host allocation failed                                */
+    FSC_ERR_CUDA = 4,        /* CUDA runtime error / no device                                  */
+    FSC_ERR_NO_KEYS = 5,     /* server keys not uploaded yet                                    */
+    FSC_ERR_COMM = 6,        /* level-exchange callback failed (multi-GPU)                      */
+    FSC_ERR_INTERNAL = 7
+};
+
+/* Replaces tfhe::ConfigBuilder::default().build() (src/biguint.rs:276, src/perf_test.rs:9,
+ * src/schnorr.rs:441): the PARAM_MESSAGE_2_CARRY_2_KS_PBS constants as plain data.            */
+typedef struct {
+    uint32_t lwe_dim;          /* n                                                   */
+    uint32_t glwe_dim;         /* k  (kernels require 1)                              */
+    uint32_t poly_size;        /* N  (kernels require 2048)                           */
+    uint32_t pbs_base_log;     /* log2 beta_pbs                                       */
+    uint32_t pbs_level;        /* l_pbs (kernels require 1)                           */
+    uint32_t ks_base_log;      /* log2 beta_ks                                        */
+    uint32_t ks_level;         /* l_ks                                                */
+    uint32_t message_modulus;  /* 4                                                   */
+    uint32_t carry_modulus;    /* 4                                                   */
+    uint32_t acc_bits;         /* blind-rotation accumulator width: 64 (default if 0) or 32 */
+} fsc_params;
+
+typedef struct fsc_ctx fsc_ctx;          /* replaces the thread-local tfhe ServerKey              */
+typedef struct fsc_lwe fsc_lwe;          /* device array of LWE ciphertexts                       */
+typedef struct fsc_luts fsc_luts;        /* device array of LUT accumulator polynomials           */
+
+/* ---- context & keys ------------------------------------------------------------------ */
+/* `stream` is an existing cudaStream_t cast to uintptr_t (e.g. torch.cuda.current_stream().cuda_stream)
+ * or 0 to let the context create its own non-blocking stream.                                    */
+fsc_status fsc_ctx_create(const fsc_params *params, int32_t device, uintptr_t stream, fsc_ctx **out);
+fsc_status fsc_ctx_destroy(fsc_ctx *ctx);
+const char *fsc_last_error(const fsc_ctx *ctx);
+fsc_status fsc_get_params(const fsc_ctx *ctx, fsc_params *out);
+fsc_status fsc_sync(fsc_ctx *ctx);
+
+/* Replaces tfhe::set_server_key (src/biguint.rs:278).  bsk_std: [n][k+1][l][k+1][N] standard-domain
+ * GGSW rows; ksk: [k*N][l_ks][n+1].  The bootstrapping key is converted to the Fourier domain on
+ * the device; the host buffers may be released when the call returns.                            */
+fsc_status fsc_keys_upload(fsc_ctx *ctx, const uint64_t *bsk_std, size_t bsk_words,
+                           const uint64_t *ksk, size_t ksk_words);
+
+/* ---- ciphertext buffers --------------------------------------------------------------- */
+enum { FSC_LWE_BIG = 0, FSC_LWE_SMALL = 1 };
+fsc_status fsc_lwe_alloc(fsc_ctx *ctx, uint32_t kind, size_t count, fsc_lwe **out);
+fsc_status fsc_lwe_free(fsc_ctx *ctx, fsc_lwe *a);
+fsc_status fsc_lwe_upload(fsc_ctx *ctx, fsc_lwe *dst, size_t first, const uint64_t *host, size_t count);
+fsc_status fsc_lwe_download(fsc_ctx *ctx, const fsc_lwe *src, size_t first, uint64_t *host, size_t count);
+fsc_status fsc_lwe_info(const fsc_lwe *a, uint32_t *kind, size_t *count, size_t *words_per_ct, void **device_ptr);
+
+/* ---- lookup tables --------------------------------------------------------------------- */
+/* tables: n_luts x (message_modulus*carry_modulus) function values f(0..15); the library builds the
+ * redundant, half-box-rotated accumulator polynomials (what tfhe's generate_lookup_table does).  */
+fsc_status fsc_luts_from_tables(fsc_ctx *ctx, const uint64_t *tables, size_t n_luts, fsc_luts **out);
+/* polys: n_luts x N torus coefficients, used as given.                                           */
+fsc_status fsc_luts_upload(fsc_ctx *ctx, const uint64_t *polys, size_t n_luts, fsc_luts **out);
+fsc_status fsc_luts_free(fsc_ctx *ctx, fsc_luts *l);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+/* lut_idx: host array of `count` indices into `luts`, or NULL for LUT 0 everywhere.
+ * in/out ranges: ciphertexts [in_first, in_first+count) -> [out_first, out_first+count).        */
+fsc_status fsc_keyswitch_batch(fsc_ctx *ctx, const fsc_lwe *in_big, size_t in_first,
+                               fsc_lwe *out_small, size_t out_first, size_t count);
+fsc_status fsc_pbs_batch(fsc_ctx *ctx, const fsc_lwe *in_small, size_t in_first, const fsc_luts *luts,
+                         const uint32_t *lut_idx, fsc_lwe *out_big, size_t out_first, size_t count);
+/* shortint apply_lookup_table over a batch: keyswitch then PBS then sample extraction.           */
+fsc_status fsc_ks_pbs_batch(fsc_ctx *ctx, const fsc_lwe *in_big, size_t in_first, const fsc_luts *luts,
+                            const uint32_t *lut_idx, fsc_lwe *out_big, size_t out_first, size_t count);
+
+/* Host-buffer convenience (the end-to-end call bench.py times as `e2e`): upload `count` big
+ * ciphertexts, keyswitch + PBS, download the results.                                            */
+fsc_status fsc_apply_lut_host(fsc_ctx *ctx, const uint64_t *in_big_host, const fsc_luts *luts,
+                              const uint32_t *lut_idx, uint64_t *out_big_host, size_t count);
+
+/* ---- measurement & test hooks ---------------------------------------------------------- */
+/* CUDA-event timer on the context's stream.                                                      */
+fsc_status fsc_timer_start(fsc_ctx *ctx);
+fsc_status fsc_timer_stop(fsc_ctx *ctx, float *elapsed_ms);     /* synchronises */
+/* number of kernels this context has launched so far                                             */
+fsc_status fsc_launch_count(const fsc_ctx *ctx, uint64_t *out);
+/* Measures the device's sustained FP64 FMA rate (TFLOP/s, 2 flops per FMA) with a register-resident
+ * FMA-chain kernel: the denominator of the blind rotation's compute roofline.                   */
+fsc_status fsc_measure_fp64_peak(fsc_ctx *ctx, double *tflops);
+/* c = a * b (negacyclic, mod 2^64) through the blind rotation's own FFT; a: count*N torus words,
+ * b: count*N small signed integers (|b| < 2^23).  Host buffers.                                  */
+fsc_status fsc_debug_negacyclic_mul(fsc_ctx *ctx, const uint64_t *a, const int64_t *b, uint64_t *c, size_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FHE_SIGN_CUDA_H */

@@ -1,0 +1,168 @@
+"""Parity tests of the CUDA hot path against the CPU oracle, through the C ABI (run with -m gpu).
+
+Keyswitch is integer work: bit-exact.  PBS outputs are not bit-comparable between two f64 FFT
+implementations (rounding differences are re-randomised by the gadget decomposition of the next CMUX
+step), so the bar there is the one the reference's own tests use — identical decrypted values —
+plus noise statistics against the oracle's and against the parameter set's budget."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _noise(K, ct, expect_msgs):
+    return (K.phase_big(ct) - K.encode(expect_msgs)).astype(np.int64).astype(np.float64) / 2.0**64
+
+
+def test_fft_hook_matches_exact_negacyclic_product(gpu_ctx, orc, rng):
+    ctx = gpu_ctx("toy")
+    a = rng.integers(0, 2**64, (5, 2048), dtype=np.uint64)
+    b = rng.integers(-2**22, 2**22, (5, 2048), dtype=np.int64)
+    b[0] = 0; b[0, 0] = 1                                  # identity
+    b[1] = 0; b[1, 2047] = 1                               # X^(N-1): exercises the negacyclic wrap
+    c = ctx.debug_negacyclic_mul(a, b)
+    for i in range(5):
+        d = (c[i] - orc.negacyclic_mul_exact(a[i], b[i])).astype(np.int64)
+        assert np.abs(d).max() < 2**43, i
+
+
+@pytest.mark.parametrize("preset,count", [("toy", 1), ("toy", 70), ("2_2_gaussian", 33), ("2_2_tuniform", 16)])
+def test_keyswitch_bit_exact(gpu_ctx, oracle_keys, rng, preset, count):
+    from fhe_sign_b200.capi import LWE_BIG, LWE_SMALL
+    K, ctx = oracle_keys(preset), gpu_ctx(preset)
+    ct = K.encrypt_msgs(rng.integers(0, 16, count).astype(np.uint64))
+    ct[0, :8] = [0, 2**64 - 1, 2**63, 2**63 - 1, 2**48, 2**48 - 1, 3 << 47, 1 << 60]   # decomposition edge values
+    din, dout = ctx.lwe(LWE_BIG, count).upload(ct), ctx.lwe(LWE_SMALL, count)
+    ctx.keyswitch(din, dout)
+    got = dout.download()
+    assert np.array_equal(got, K.keyswitch(ct))
+    din.free(); dout.free()
+
+
+@pytest.mark.parametrize("acc_bits", [64, 32])
+@pytest.mark.parametrize("preset", ["toy", "2_2_gaussian", "2_2_tuniform"])
+def test_pbs_all_messages_all_luts(gpu_ctx, oracle_keys, rng, preset, acc_bits):
+    from fhe_sign_b200.capi import LWE_BIG
+    K, ctx = oracle_keys(preset), gpu_ctx(preset, acc_bits)
+    tables = np.stack([np.arange(16), (np.arange(16) * 3 + 1) % 16, rng.integers(0, 16, 16),
+                       [((i >> 2) * (i & 3)) % 4 for i in range(16)]]).astype(np.uint64)
+    luts = ctx.luts_from_tables(tables)
+    m = np.tile(np.arange(16), 4).astype(np.uint64)
+    idx = np.repeat(np.arange(4), 16).astype(np.uint32)
+    ct = K.encrypt_msgs(m)
+    din, dout = ctx.lwe(LWE_BIG, m.size).upload(ct), ctx.lwe(LWE_BIG, m.size)
+    ctx.ks_pbs(din, luts, idx, dout)
+    out = dout.download()
+    assert (K.decrypt_msgs(out) == tables[idx, m]).all()
+    assert np.abs(_noise(K, out, tables[idx, m])).max() < 2.0**-7
+    din.free(); dout.free(); luts.free()
+
+
+def test_lut_polynomials_match_oracle(gpu_ctx, oracle_keys, rng):
+    """fsc_luts_from_tables builds the same accumulator the oracle does: PBS through uploaded oracle
+    polynomials and through library-built ones decrypt identically."""
+    from fhe_sign_b200.capi import LWE_BIG
+    K, ctx = oracle_keys("toy"), gpu_ctx("toy")
+    table = rng.integers(0, 16, 16).astype(np.uint64)
+    l1, l2 = ctx.luts_from_tables(table), ctx.luts_upload(K.make_lut(table))
+    m = np.arange(16).astype(np.uint64)
+    din = ctx.lwe(LWE_BIG, 16).upload(K.encrypt_msgs(m))
+    o1, o2 = ctx.lwe(LWE_BIG, 16), ctx.lwe(LWE_BIG, 16)
+    ctx.ks_pbs(din, l1, None, o1)
+    ctx.ks_pbs(din, l2, None, o2)
+    assert np.array_equal(o1.download(), o2.download())      # same kernel, same inputs: deterministic
+    assert (K.decrypt_msgs(o1.download()) == table[m]).all()
+
+
+@pytest.mark.parametrize("acc_bits", [64, 32])
+def test_pbs_noise_matches_oracle_toy(gpu_ctx, oracle_keys, rng, acc_bits):
+    """Same inputs through the GPU and through the oracle: equal decryptions, equal noise level."""
+    from fhe_sign_b200.capi import LWE_SMALL, LWE_BIG
+    K, ctx = oracle_keys("toy"), gpu_ctx("toy", acc_bits)
+    count = 512
+    m = rng.integers(0, 16, count).astype(np.uint64)
+    small = K.keyswitch(K.encrypt_msgs(m))
+    luts = ctx.luts_from_tables(np.arange(16))
+    din, dout = ctx.lwe(LWE_SMALL, count).upload(small), ctx.lwe(LWE_BIG, count)
+    ctx.pbs(din, luts, None, dout)
+    out = dout.download()
+    ref = K.pbs(small, K.make_lut(np.arange(16)))
+    assert (K.decrypt_msgs(out) == m).all() and (K.decrypt_msgs(ref) == m).all()
+    s_gpu, s_ref = _noise(K, out, m).std(), _noise(K, ref, m).std()
+    assert s_gpu < 1.15 * s_ref, (s_gpu, s_ref)
+
+
+def test_apply_lut_host_ragged_and_empty(gpu_ctx, oracle_keys, rng):
+    K, ctx = oracle_keys("toy"), gpu_ctx("toy")
+    luts = ctx.luts_from_tables(np.stack([np.arange(16), 15 - np.arange(16)]))
+    for count in (0, 1, 37):
+        m = rng.integers(0, 16, count).astype(np.uint64)
+        idx = rng.integers(0, 2, count).astype(np.uint32)
+        out = ctx.apply_lut_host(K.encrypt_msgs(m).reshape(count, 2049), luts, idx)
+        assert out.shape == (count, 2049)
+        assert (K.decrypt_msgs(out) == np.where(idx == 0, m, 15 - m)).all()
+
+
+def test_padding_bit_negates(gpu_ctx, oracle_keys):
+    """Messages with the padding bit set (m >= 16) come out negated: the negacyclic property every
+    radix circuit has to respect."""
+    K, ctx = oracle_keys("toy"), gpu_ctx("toy")
+    luts = ctx.luts_from_tables(np.arange(16))
+    m = np.arange(16, 32).astype(np.uint64)
+    out = ctx.apply_lut_host(K.encrypt_msgs(m), luts)
+    assert (K.decrypt_msgs(out) == (32 - (m - 16)) % 32).all()
+
+
+def test_error_codes(gpu_ctx, oracle_keys):
+    import fhe_sign_b200 as fsb
+    from fhe_sign_b200.capi import LWE_BIG, LWE_SMALL
+    ctx = fsb.Context(fsb.Params.preset("toy"))
+    luts = ctx.luts_from_tables(np.arange(16))
+    a, b = ctx.lwe(LWE_BIG, 4), ctx.lwe(LWE_BIG, 4)
+    with pytest.raises(fsb.FscError) as ei:
+        ctx.ks_pbs(a, luts, None, b)
+    assert ei.value.code == 5                                  # keys not uploaded
+    K = oracle_keys("toy")
+    with pytest.raises(fsb.FscError) as ei:
+        ctx.upload_keys(K.bsk[:-1], K.ksk)
+    assert ei.value.code == 1
+    ctx.upload_keys(K.bsk, K.ksk)
+    with pytest.raises(fsb.FscError) as ei:
+        ctx.ks_pbs(a, luts, np.array([0, 1, 0, 0], dtype=np.uint32), b)    # lut index out of range
+    assert ei.value.code == 1
+    with pytest.raises(fsb.FscError) as ei:
+        ctx.ks_pbs(a, luts, None, ctx.lwe(LWE_SMALL, 4))      # wrong kind
+    assert ei.value.code == 1
+    with pytest.raises(fsb.FscError) as ei:
+        ctx.ks_pbs(a, luts, None, b, count=5)                  # range
+    assert ei.value.code == 1
+    with pytest.raises(fsb.FscError) as ei:
+        fsb.Context(fsb.Params.preset("toy").__class__(lwe_dim=48, glwe_dim=2, poly_size=1024, pbs_base_log=23, pbs_level=1,
+                                                       ks_base_log=3, ks_level=5, message_modulus=4, carry_modulus=4, acc_bits=64))
+    assert ei.value.code == 2
+    ctx.close()
+
+
+@pytest.mark.parametrize("acc_bits", [64, 32])
+def test_noise_over_1e5_bootstraps(gpu_ctx, oracle_keys, acc_bits):
+    """north_star: PBS noise within the parameter set's variance bound over >= 1e5 bootstraps.
+    Bound: decoding radius 2^-5 at p_fail 2^-64 -> sigma_total <= 2^-5 / 9.2; a fresh PBS output
+    (noise level 1) must sit far inside it.  Also: zero decode failures over all 1e5."""
+    K, ctx = oracle_keys("2_2_gaussian"), gpu_ctx("2_2_gaussian", acc_bits)
+    table = (np.arange(16) * 7 + 3) % 16
+    luts = ctx.luts_from_tables(table)
+    rng = np.random.default_rng(5)
+    total, chunk = 102400, 12800
+    sq, fails, worst = 0.0, 0, 0.0
+    for s in range(total // chunk):
+        m = rng.integers(0, 16, chunk).astype(np.uint64)
+        out = ctx.apply_lut_host(K.encrypt_msgs(m, seed=11, stream=s * chunk), luts)
+        exp = table[m].astype(np.uint64)
+        fails += int((K.decrypt_msgs(out) != exp).sum())
+        e = _noise(K, out, exp)
+        sq += float((e * e).sum()); worst = max(worst, float(np.abs(e).max()))
+    sigma = (sq / total) ** 0.5
+    print("acc_bits=%d sigma_pbs=2^%.3f worst=2^%.3f over %d bootstraps" % (acc_bits, np.log2(sigma), np.log2(worst), total))
+    assert fails == 0
+    assert sigma < 2.0**-14.0          # measured oracle sigma is ~2^-15.1; budget for level-1 noise
+    assert worst < 2.0**-6
