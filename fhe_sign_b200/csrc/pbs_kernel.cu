@@ -12,6 +12,7 @@
 // PBS half of shortint apply_lookup_table behind every operator in src/biguint.rs:110-248.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "pbs_core.cuh"
 #include "fsc_internal.h"
 
@@ -163,6 +164,157 @@ __global__ void __launch_bounds__(64, 4) pbs_pair_kernel(const cplx* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------
+// Ring variant: one CTA = CTS ciphertexts (2 warps each).  The Fourier GGSW of every CMUX step is
+// streamed from L2 into a shared-memory ring by 1-D bulk copies (TMA, cp.async.bulk + mbarrier
+// complete_tx) issued NCH-1 chunks ahead of use by one elected lane of warp 0, so that the
+// Fourier-domain product reads the key from shared memory instead of waiting on L2 latency, and one
+// L2 read feeds all CTS ciphertexts of the CTA.
+// shared memory: acc [CTS][2][1024] pair_t<AccT> | xbuf [CTS][2][1024] cplx | ring [NCH][512] cplx |
+//                full[NCH], empty[NCH] mbarriers
+// ---------------------------------------------------------------------------------------
+constexpr int kChunkSlots = 4;                         // frequency slots per ring chunk
+constexpr int kChunkCplx = kChunkSlots * 4 * 32;       // 512 complex = 8 KiB
+constexpr int kChunksPerStep = 32 / kChunkSlots;       // 8
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void pair_barrier(int id) {      // the two warps of one ciphertext
+    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
+
+template <typename AccT, int CTS, int NCH>
+__global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
+                                                                     int n, int base_log, const uint64_t* __restrict__ luts,
+                                                                     const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
+                                                                     int count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    pair_t<AccT>* acc_all = reinterpret_cast<pair_t<AccT>*>(smem_raw);
+    cplx* xbuf_all = reinterpret_cast<cplx*>(smem_raw + (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>));
+    cplx* ring = xbuf_all + (size_t)CTS * 2 * 1024;
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)NCH * kChunkCplx);
+    uint64_t* empty = full + NCH;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NCH; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 2 * CTS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int total_chunks = n * kChunksPerStep;
+    const bool producer = threadIdx.x == 0;
+    if (producer) {
+        for (int u = 0; u < NCH && u < total_chunks; ++u) {
+            mbar_arrive_expect_tx(full + u, kChunkCplx * sizeof(cplx));
+            bulk_load(ring + (size_t)u * kChunkCplx, bsk_f + (size_t)u * kChunkCplx, kChunkCplx * sizeof(cplx), full + u);
+        }
+    }
+
+    // ---- consumers: warp (ct, p) owns polynomial p of ciphertext ct ----
+    const int ctl = warp >> 1, p = warp & 1;
+    const int c_raw = blockIdx.x * CTS + ctl;
+    const bool live = c_raw < count;
+    const int c = live ? c_raw : count - 1;            // padding warps shadow the last ciphertext, never store
+    pair_t<AccT>* acc = acc_all + (size_t)(ctl * 2 + p) * 1024;
+    cplx* xbuf = xbuf_all + (size_t)(ctl * 2 + p) * 1024;
+    const cplx* xother = xbuf_all + (size_t)(ctl * 2 + (1 - p)) * 1024;
+    const uint64_t* ct = in_small + (size_t)c * (n + 1);
+    const uint64_t* lut = luts + (size_t)(lut_idx ? lut_idx[c] : 0) * kN;
+
+    cplx s2[16];
+    lane_consts(4 * lane + 1, s2);
+    {
+        const int b = modswitch(ct[n]);
+#pragma unroll 4
+        for (int j2 = 0; j2 < 32; ++j2) {
+            const int idx = lane + 32 * j2;
+            pair_t<AccT> z; z.x = 0; z.y = 0;
+            acc[idx] = p ? lut_pair<AccT>(lut, idx, b) : z;
+        }
+    }
+    __syncwarp();
+
+    int a_chunk = 0;
+    int t = 0;                                          // ring chunk counter
+    for (int i = 0; i < n; ++i) {
+        if ((i & 31) == 0) a_chunk = (i + lane < n) ? modswitch(ct[i + lane]) : 0;
+        const int a = __shfl_sync(0xffffffffu, a_chunk, i & 31);
+        // a == 0 is not skipped: the ring is shared by all ciphertexts of the CTA; the step is an exact no-op
+
+        cplx X[32];
+        cmux_head<AccT>(lane, acc, a, base_log, X);
+        warp_fft_fwd(lane, xbuf, s2, X);
+#pragma unroll
+        for (int r = 0; r < 32; ++r) xbuf[r * 32 + lane] = X[r];
+        pair_barrier(1 + ctl);
+
+#pragma unroll
+        for (int k = 0; k < kChunksPerStep; ++k, ++t) {
+            const int stage = t % NCH;
+            mbar_wait(full + stage, (uint32_t)(t / NCH) & 1);
+            const cplx* g = ring + (size_t)stage * kChunkCplx + lane + p * 32;
+#pragma unroll
+            for (int rr = 0; rr < kChunkSlots; ++rr) {
+                const int r = k * kChunkSlots + rr;
+                const cplx o = xother[r * 32 + lane];
+                const cplx g0 = g[(rr * 4) * 32], g1 = g[(rr * 4 + 2) * 32];      // G[0][p], G[1][p]
+                const cplx x0 = p ? o : X[r];
+                const cplx x1 = p ? X[r] : o;
+                X[r].x = x0.x * g0.x - x0.y * g0.y + x1.x * g1.x - x1.y * g1.y;
+                X[r].y = x0.x * g0.y + x0.y * g0.x + x1.x * g1.y + x1.y * g1.x;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + stage);
+            if (producer && t >= 1) {
+                // refill the stage released one chunk ago with the chunk NCH-1 ahead of the current one
+                const int u = t - 1 + NCH;
+                if (u < total_chunks) {
+                    const int ps = (t - 1) % NCH;
+                    mbar_wait(empty + ps, (uint32_t)((t - 1) / NCH) & 1);
+                    mbar_arrive_expect_tx(full + ps, kChunkCplx * sizeof(cplx));
+                    bulk_load(ring + (size_t)ps * kChunkCplx, bsk_f + (size_t)u * kChunkCplx, kChunkCplx * sizeof(cplx), full + ps);
+                }
+            }
+        }
+        pair_barrier(1 + ctl);
+
+        warp_fft_inv(lane, xbuf, s2, X);
+        cmux_tail<AccT>(lane, acc, X);
+        __syncwarp();
+    }
+    pair_barrier(1 + ctl);
+
+    if (live) {
+        uint64_t* out = out_big + (size_t)c * (kN + 1);
+        const pair_t<AccT>* mask = acc_all + (size_t)(ctl * 2) * 1024;
+        for (int j = (p * 32 + lane); j <= kN; j += 64) out[j] = extract_word<AccT>(mask, mask + 1024, j);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Test hook: c = a (torus) * b (small integers), negacyclic, through the kernel's own FFT.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) negacyclic_mul_kernel(const uint64_t* __restrict__ a, const int64_t* __restrict__ b,
@@ -203,8 +355,8 @@ void launch_bsk_convert(const uint64_t* bsk, void* out, int n, cudaStream_t st) 
 }
 
 template <typename AccT>
-static void launch_pbs_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
-                         const uint32_t* lut_idx, uint64_t* out_big, int count, cudaStream_t st) {
+static void launch_pbs_pair_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
+                              const uint32_t* lut_idx, uint64_t* out_big, int count, cudaStream_t st) {
     const size_t smem = 2 * 1024 * sizeof(pair_t<AccT>) + 2 * 1024 * sizeof(cplx);
     static bool configured = false;
     if (!configured) {
@@ -215,11 +367,40 @@ static void launch_pbs_t(const void* bsk_f, const uint64_t* in_small, int n, int
                                                     lut_idx, out_big, count);
 }
 
+template <typename AccT, int CTS, int NCH>
+static void launch_pbs_ring_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
+                              const uint32_t* lut_idx, uint64_t* out_big, int count, cudaStream_t st) {
+    const size_t smem = (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>) + (size_t)CTS * 2 * 1024 * sizeof(cplx) +
+                        (size_t)NCH * kChunkCplx * sizeof(cplx) + 2 * NCH * sizeof(uint64_t);
+    static bool configured = false;
+    if (!configured) {
+        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_ring_kernel<AccT, CTS, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int grid = (count + CTS - 1) / CTS;
+    pbs_ring_kernel<AccT, CTS, NCH><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log,
+                                                                        luts, lut_idx, out_big, count);
+}
+
+static int pbs_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FSC_PBS_VARIANT");      // "pair" | "ring" (default)
+        v = (e && e[0] == 'p') ? 0 : 1;
+    }
+    return v;
+}
+
 void launch_pbs(int acc_bits, const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
                 const uint32_t* lut_idx, uint64_t* out_big, int count, cudaStream_t st) {
     if (count <= 0) return;
-    if (acc_bits == 32) launch_pbs_t<uint32_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, count, st);
-    else launch_pbs_t<uint64_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, count, st);
+    if (pbs_variant() == 0) {
+        if (acc_bits == 32) launch_pbs_pair_t<uint32_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, count, st);
+        else launch_pbs_pair_t<uint64_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, count, st);
+    } else {
+        if (acc_bits == 32) launch_pbs_ring_t<uint32_t, 4, 4>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, count, st);
+        else launch_pbs_ring_t<uint64_t, 3, 4>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, count, st);
+    }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -109,6 +109,59 @@ fsc_status fsc_ks_pbs_batch(fsc_ctx *ctx, const fsc_lwe *in_big, size_t in_first
 fsc_status fsc_apply_lut_host(fsc_ctx *ctx, const uint64_t *in_big_host, const fsc_luts *luts,
                               const uint32_t *lut_idx, uint64_t *out_big_host, size_t count);
 
+/* ---- radix integers: the FheUint8/32/64 operator surface of the reference ------------------ */
+/* A radix value is a little-endian vector of big-LWE blocks carrying 2 message bits each
+ * (FheUint8/32/64 = 4/16/32 blocks; a 256-bit integer = 128 blocks).  Values live on the device
+ * between operators; every operator returns a NEW handle and never modifies its inputs (the
+ * reference clones every operand: src/biguint.rs:135-137,221-222).  Wrapping semantics and the
+ * shift-amount-modulo-width rule are those of the reference's tfhe types (src/biguint.rs:469-499). */
+typedef struct fsc_radix fsc_radix;
+
+enum {
+    FSC_OP_ADD = 0,   /* +   src/biguint.rs:138,148,236,243,248 ; src/perf_test.rs:28 ; scalar: src/schnorr.rs:604 */
+    FSC_OP_SUB = 1,
+    FSC_OP_MUL = 2,   /* *   src/biguint.rs:223 ; src/perf_test.rs:32 ; scalar: src/schnorr.rs:588              */
+    FSC_OP_MIN = 3,   /* FheOrd::min   src/perf_test.rs:44                                                      */
+    FSC_OP_MAX = 4,
+    FSC_OP_SHR = 5,   /* >>  encrypted amount: src/perf_test.rs:36 ; scalar amount: src/biguint.rs:110,141      */
+    FSC_OP_SHL = 6,
+    FSC_OP_AND = 7,   /* &   scalar mask: src/biguint.rs:116,143 ; src/perf_test.rs:48                          */
+    FSC_OP_OR = 8,
+    FSC_OP_XOR = 9,
+    FSC_OP_LT = 10,   /* result: one block holding 0 / 1                                                         */
+    FSC_OP_EQ = 11,
+    FSC_OP_DIV = 12,  /* /   scalar divisor: src/perf_test.rs:54 (division by zero -> FSC_ERR_BAD_ARG)          */
+    FSC_OP_REM = 13
+};
+
+/* FheUintN::try_encrypt happens on the client (src/biguint.rs:26); the server receives the blocks.
+ * host_blocks: n_blocks * (k*N+1) words, least significant block first.                          */
+fsc_status fsc_radix_from_lwe(fsc_ctx *ctx, const uint64_t *host_blocks, size_t n_blocks, fsc_radix **out);
+/* Brings the blocks back for FheUintN::decrypt (src/biguint.rs:70); synchronises.                */
+fsc_status fsc_radix_to_lwe(fsc_ctx *ctx, fsc_radix *r, uint64_t *host_blocks);
+/* Noiseless encryption of a plaintext constant (little-endian bytes), e.g. the zero digits of Mul. */
+fsc_status fsc_radix_trivial(fsc_ctx *ctx, const uint8_t *value_le, size_t n_bytes, size_t n_blocks, fsc_radix **out);
+fsc_status fsc_radix_clone(fsc_ctx *ctx, const fsc_radix *a, fsc_radix **out);
+fsc_status fsc_radix_free(fsc_ctx *ctx, fsc_radix *a);
+fsc_status fsc_radix_len(const fsc_radix *a, size_t *n_blocks);
+/* out = a <op> b for FSC_OP_ADD..FSC_OP_EQ (ciphertext, ciphertext).                              */
+fsc_status fsc_radix_binary(fsc_ctx *ctx, uint32_t op, const fsc_radix *a, const fsc_radix *b, fsc_radix **out);
+/* out = a <op> scalar for ADD, MUL, AND, DIV, REM, SHR, SHL; the scalar is little-endian bytes of any
+ * length (for SHR/SHL it is the bit count, taken modulo the width of a).                          */
+fsc_status fsc_radix_scalar(fsc_ctx *ctx, uint32_t op, const fsc_radix *a, const uint8_t *scalar_le, size_t n_bytes, fsc_radix **out);
+/* a * b without wrapping at |a| blocks: out_blocks result blocks (e.g. 256 for a 256x256-bit product). */
+fsc_status fsc_radix_mul_wide(fsc_ctx *ctx, const fsc_radix *a, const fsc_radix *b, size_t out_blocks, fsc_radix **out);
+/* FheUintM::cast_from (src/biguint.rs:110,116,135-137): truncate or zero-extend; no device work.  */
+fsc_status fsc_radix_cast(fsc_ctx *ctx, const fsc_radix *a, size_t n_blocks, fsc_radix **out);
+fsc_status fsc_radix_slice(fsc_ctx *ctx, const fsc_radix *a, size_t first, size_t n_blocks, fsc_radix **out);
+fsc_status fsc_radix_concat(fsc_ctx *ctx, const fsc_radix *const *parts, size_t n_parts, fsc_radix **out);
+/* sum of n_operands values, wrapping at n_blocks (one carry-save reduction + one carry propagation). */
+fsc_status fsc_radix_sum(fsc_ctx *ctx, const fsc_radix *const *operands, size_t n_operands, size_t n_blocks, fsc_radix **out);
+/* cond ? if_true : if_false; cond is a one-block value holding 0 / 1 (FSC_OP_LT / FSC_OP_EQ output). */
+fsc_status fsc_radix_select(fsc_ctx *ctx, const fsc_radix *cond, const fsc_radix *if_true, const fsc_radix *if_false, fsc_radix **out);
+/* bootstraps and PBS levels issued by the radix layer so far on this context                      */
+fsc_status fsc_radix_stats(const fsc_ctx *ctx, uint64_t *pbs_count, uint64_t *level_count);
+
 /* ---- measurement & test hooks ---------------------------------------------------------- */
 /* CUDA-event timer on the context's stream.                                                      */
 fsc_status fsc_timer_start(fsc_ctx *ctx);

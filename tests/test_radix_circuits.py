@@ -1,0 +1,178 @@
+"""Every radix circuit of fhe_sign_b200/csrc/radix.cpp on the CPU mock backend: results against
+Python integers (the plaintext contract of the reference's FheUint operators), no
+bootstrap input ever touching the padding bit, noise budget respected (the evaluator throws)."""
+import random
+
+import pytest
+
+from mock_radix import MockRadix
+
+
+@pytest.fixture(scope="module")
+def M():
+    return MockRadix()
+
+
+def _rand(rnd, bits):
+    k = rnd.choice([0, 1, 2, 3])
+    if k == 0:
+        return rnd.getrandbits(bits)
+    if k == 1:
+        return (1 << bits) - 1 - rnd.getrandbits(bits // 4)
+    if k == 2:
+        return rnd.getrandbits(bits // 2)
+    return rnd.choice([0, 1, (1 << bits) - 1, 1 << (bits - 1)])
+
+
+@pytest.mark.parametrize("bits", [8, 32, 64])
+def test_add_sub_mul_wrap(M, bits):
+    rnd = random.Random(bits)
+    n, mask = bits // 2, (1 << bits) - 1
+    for _ in range(40):
+        x, y = _rand(rnd, bits), _rand(rnd, bits)
+        a, b = M.enc(x, n), M.enc(y, n)
+        assert M.dec(a + b) == (x + y) & mask
+        assert M.dec(a - b) == (x - y) & mask
+        assert M.dec(a * b) == (x * y) & mask
+    assert M.counters()["violations"] == 0
+
+
+def test_reference_kats_on_u32_and_u64(M):
+    """decrypted known answers of the reference's tests (src/biguint.rs:429-527)."""
+    F = 0xFFFFFFFF
+    a64 = lambda v: M.api.cast(M.enc(v, 16), 32)
+    s = a64(5) + a64(3)
+    assert M.dec(M.api.cast(s >> 32, 16)) == 0 and M.dec(M.api.cast(s & F, 16)) == 8
+    s = a64(F) + a64(1)
+    assert M.dec(M.api.cast(s >> 32, 16)) == 1 and M.dec(M.api.cast(s & F, 16)) == 0
+    s = a64(F) + a64(F)
+    assert M.dec(M.api.cast(s >> 32, 16)) == 1 and M.dec(M.api.cast(s & F, 16)) == 0xFFFFFFFE
+    # FheUint32 overflow wraps; a shift by the full width is a shift by 0 (src/biguint.rs:469-499)
+    w = M.enc(F, 16) + M.enc(1, 16)
+    assert M.dec(w) == 0
+    t = M.enc(F, 16) + M.enc(F, 16)
+    assert M.dec(t >> 32) == 4294967294 and M.dec(t & F) == 4294967294
+    p = a64(F) * a64(2)
+    assert M.dec(p >> 32) == 1 and M.dec(p & F) == 0xFFFFFFFE
+    # scalar ops of src/schnorr.rs:575-607
+    assert M.dec(M.enc(123, 16) * 456) == 56088 and M.dec(M.enc(123, 16) + 456) == 579
+    assert M.counters()["violations"] == 0
+
+
+def test_perf_test_op_chain(M):
+    """src/perf_test.rs:14-75 with its operands: ((1344 >> 5) as u8).min(7) & 1 == 1, 1344 / 5 == 268."""
+    a, b, c = M.enc(1344, 16), M.enc(5, 16), M.enc(7, 4)
+    assert M.dec(a + b) == 1349
+    assert M.dec(a * b) == 6720
+    sh = a >> b
+    assert M.dec(sh) == 42
+    as8 = M.api.cast(sh, 4)
+    mn = M.api.min(as8, c)
+    assert M.dec(mn) == 7
+    assert M.dec(mn & 1) == 1
+    assert M.dec(a // 5) == 268
+    assert M.counters()["violations"] == 0
+
+
+@pytest.mark.parametrize("bits", [8, 32])
+def test_shifts(M, bits):
+    rnd = random.Random(7)
+    n, mask = bits // 2, (1 << bits) - 1
+    for _ in range(12):
+        x = _rand(rnd, bits)
+        a = M.enc(x, n)
+        for s in (0, 1, 2, 3, bits // 2 - 1, bits - 1, bits, bits + 3):
+            assert M.dec(a >> s) == x >> (s % bits), (x, s)
+            assert M.dec(a << s) == (x << (s % bits)) & mask, (x, s)
+        amt = rnd.getrandbits(bits)
+        e = M.enc(amt, n)
+        assert M.dec(a >> e) == x >> (amt % bits)
+        assert M.dec(a << e) == (x << (amt % bits)) & mask
+    assert M.counters()["violations"] == 0
+
+
+def test_compare_select_minmax(M):
+    rnd = random.Random(3)
+    for bits in (8, 32):
+        n = bits // 2
+        for _ in range(30):
+            x, y = _rand(rnd, bits), _rand(rnd, bits)
+            if rnd.random() < 0.2:
+                y = x
+            a, b = M.enc(x, n), M.enc(y, n)
+            assert M.dec(M.api.lt(a, b)) == int(x < y)
+            assert M.dec(M.api.eq(a, b)) == int(x == y)
+            assert M.dec(M.api.min(a, b)) == min(x, y)
+            assert M.dec(M.api.max(a, b)) == max(x, y)
+            assert M.dec(M.api.select(M.api.lt(a, b), a, b)) == min(x, y)
+    assert M.counters()["violations"] == 0
+
+
+def test_bitops_and_masks(M):
+    rnd = random.Random(4)
+    for _ in range(20):
+        x, y = rnd.getrandbits(32), rnd.getrandbits(32)
+        a, b = M.enc(x, 16), M.enc(y, 16)
+        assert M.dec(a & b) == x & y
+        assert M.dec(M.api.binary("or_", a, b)) == x | y
+        assert M.dec(M.api.binary("xor", a, b)) == x ^ y
+        assert M.dec(a & y) == x & y
+    assert M.counters()["violations"] == 0
+
+
+@pytest.mark.parametrize("bits", [8, 32, 64])
+def test_scalar_mul_div_rem(M, bits):
+    rnd = random.Random(bits + 1)
+    n, mask = bits // 2, (1 << bits) - 1
+    for _ in range(25):
+        x = _rand(rnd, bits)
+        a = M.enc(x, n)
+        c = _rand(rnd, bits)
+        assert M.dec(a * c) == (x * c) & mask
+        assert M.dec(a + c) == (x + c) & mask
+        d = rnd.choice([1, 2, 3, 5, 7, 10, 255, 256, 641, (1 << (bits - 1)) + 1, mask, rnd.getrandbits(bits) | 1, rnd.getrandbits(bits // 2) + 1])
+        assert M.dec(a // d) == x // d, (x, d)
+        assert M.dec(a % d) == x % d, (x, d)
+    with pytest.raises(RuntimeError):
+        M.enc(5, n) // 0
+    assert M.counters()["violations"] == 0
+
+
+def test_wide_mul_sum_and_256_bit(M):
+    rnd = random.Random(9)
+    for _ in range(4):
+        x, y, z = rnd.getrandbits(256), rnd.getrandbits(256), rnd.getrandbits(256)
+        a, b, c = M.enc(x, 128), M.enc(y, 128), M.enc(z, 128)
+        prod = M.api.mul_wide(a, b, 256)
+        assert M.dec(prod) == x * y
+        s = M.api.sum([prod, M.api.cast(c, 257)], 257)
+        assert M.dec(s) == x * y + z
+    ops = [M.enc(rnd.getrandbits(64), 32) for _ in range(13)]
+    vals = [M.dec(o) for o in ops]
+    assert M.dec(M.api.sum(ops, 40)) == sum(vals)
+    assert M.dec(M.api.sum(ops, 32)) == sum(vals) & (2**64 - 1)
+    n_order = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141      # src/scalar.rs:8
+    x = rnd.getrandbits(512)
+    assert M.dec(M.enc(x, 257) % n_order) == x % n_order
+    assert M.counters()["violations"] == 0
+
+
+def test_slots_are_released(M):
+    import gc
+    gc.collect()
+    before = M.counters()["live_slots"]
+    a, b = M.enc(123456789, 16), M.enc(987654321, 16)
+    c = a * b + a
+    assert M.dec(c) == (123456789 * 987654321 + 123456789) & 0xFFFFFFFF
+    del a, b, c
+    gc.collect()
+    assert M.counters()["live_slots"] == before
+
+
+def test_trivial_operands_cost_nothing(M):
+    p0, _ = M.api.stats()
+    a = M.api.trivial(1234, 16)
+    b = M.api.trivial(77, 16)
+    assert M.dec(a + b) == 1311 and M.dec(a * b) == 1234 * 77
+    p1, _ = M.api.stats()
+    assert p1 == p0
