@@ -94,6 +94,8 @@ EXPORTS = ["fsc_ctx_create", "fsc_ctx_destroy", "fsc_last_error", "fsc_get_param
            "fsc_luts_from_tables", "fsc_luts_upload", "fsc_luts_free", "fsc_keyswitch_batch", "fsc_pbs_batch",
            "fsc_ks_pbs_batch", "fsc_apply_lut_host", "fsc_timer_start", "fsc_timer_stop", "fsc_launch_count",
            "fsc_debug_negacyclic_mul", "fsc_measure_fp64_peak"]
+from .radix import RADIX_EXPORTS  # noqa: E402
+EXPORTS = EXPORTS + RADIX_EXPORTS
 
 
 def _ptr(a):
@@ -169,6 +171,14 @@ class Context:
 
     def sync(self):
         self._check(self.L.fsc_sync(self.h))
+
+    @property
+    def radix(self):
+        """Radix-integer operator surface (FheUint8/32/64 look-alikes); available once keys are uploaded."""
+        if getattr(self, "_radix", None) is None:
+            from .radix import RadixApi
+            self._radix = RadixApi(self.L, self.h, self._check, alive=lambda: bool(getattr(self, "h", None)))
+        return self._radix
 
     def upload_keys(self, bsk_std, ksk):
         bsk_std = np.ascontiguousarray(bsk_std, dtype=np.uint64)

@@ -42,7 +42,8 @@ struct Engine {
     void ensure_pinned(size_t bytes);
     const uint32_t* stage_lut_idx(const uint32_t* lut_idx, size_t count, const Luts* luts);
     void keyswitch(const uint64_t* in_big, uint64_t* out_small, size_t count);
-    void pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut_idx_dev, uint64_t* out_big, size_t count);
+    void pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut_idx_dev, uint64_t* out_big, size_t count,
+             const int32_t* out_idx_dev = nullptr);
     void ks_pbs(const uint64_t* in_big, const Luts* luts, const uint32_t* lut_idx_dev, uint64_t* out_big, size_t count);
 };
 

@@ -8,6 +8,8 @@
 
 #include "fsc_internal.h"
 #include "engine.h"
+#include "ctx.h"
+#include "radix_cuda.h"
 
 namespace fsc {
 
@@ -140,11 +142,12 @@ void Engine::keyswitch(const uint64_t* in_big, uint64_t* out_small, size_t count
     FSC_CUDA_CHECK(cudaGetLastError());
 }
 
-void Engine::pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut_idx_dev, uint64_t* out_big, size_t count) {
+void Engine::pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut_idx_dev, uint64_t* out_big, size_t count,
+                 const int32_t* out_idx_dev) {
     use();
     if (!bsk_f) throw Error(FSC_ERR_NO_KEYS, "server keys not uploaded");
     launch_pbs((int)p.acc_bits, bsk_f, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, out_big,
-               (int)count, stream);
+               out_idx_dev, (int)count, stream);
     ++launches;
     FSC_CUDA_CHECK(cudaGetLastError());
 }
@@ -163,10 +166,6 @@ void Engine::ks_pbs(const uint64_t* in_big, const Luts* luts, const uint32_t* lu
 using fsc::Engine;
 using fsc::Error;
 
-struct fsc_ctx {
-    Engine* eng = nullptr;
-    std::string err;
-};
 struct fsc_lwe {
     uint32_t kind;
     size_t count, words;
@@ -187,6 +186,11 @@ struct fsc_luts : fsc::Luts {};
 
 extern "C" {
 
+fsc_status fsc_map_exception(const std::exception& e) {
+    const Error* fe = dynamic_cast<const Error*>(&e);
+    return fe ? fe->code : FSC_ERR_INTERNAL;
+}
+
 fsc_status fsc_ctx_create(const fsc_params* params, int32_t device, uintptr_t stream, fsc_ctx** out) {
     if (!params || !out) { fsc::g_create_error = "null argument"; return FSC_ERR_BAD_ARG; }
     *out = nullptr;
@@ -194,6 +198,7 @@ fsc_status fsc_ctx_create(const fsc_params* params, int32_t device, uintptr_t st
     try {
         c = new fsc_ctx();
         c->eng = new Engine(*params, device, stream);
+        c->params = c->eng->p;
         *out = c;
         return FSC_OK;
     } catch (const Error& e) {
@@ -207,7 +212,7 @@ fsc_status fsc_ctx_create(const fsc_params* params, int32_t device, uintptr_t st
 
 fsc_status fsc_ctx_destroy(fsc_ctx* ctx) {
     if (!ctx) return FSC_ERR_BAD_ARG;
-    try { delete ctx->eng; } catch (...) {}
+    try { delete ctx->ev; delete ctx->rb; delete ctx->eng; } catch (...) {}
     delete ctx;
     return FSC_OK;
 }
@@ -230,6 +235,10 @@ fsc_status fsc_sync(fsc_ctx* ctx) {
 fsc_status fsc_keys_upload(fsc_ctx* ctx, const uint64_t* bsk_std, size_t bsk_words, const uint64_t* ksk, size_t ksk_words) {
     FSC_API_BEGIN(ctx)
     ctx->eng->upload_keys(bsk_std, bsk_words, ksk, ksk_words);
+    if (!ctx->rb) {
+        ctx->rb = fsc::make_cuda_backend(ctx->eng);
+        ctx->ev = new fsc::Evaluator(ctx->rb);
+    }
     FSC_API_END(ctx)
 }
 

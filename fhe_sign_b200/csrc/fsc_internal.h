@@ -31,7 +31,8 @@ struct Error : std::runtime_error {
 void pbs_init_constants();
 void launch_bsk_convert(const uint64_t* bsk_std, void* bsk_fourier, int n, cudaStream_t st);
 void launch_pbs(int acc_bits, const void* bsk_fourier, const uint64_t* in_small, int n, int base_log,
-                const uint64_t* luts, const uint32_t* lut_idx, uint64_t* out_big, int count, cudaStream_t st);
+                const uint64_t* luts, const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count,
+                cudaStream_t st);
 void launch_negacyclic_mul(const uint64_t* a, const int64_t* b, uint64_t* c, int count, cudaStream_t st);
 
 double launch_fp64_peak(double* sink, int sm_count, int iters, cudaStream_t st);
@@ -39,5 +40,10 @@ double launch_fp64_peak(double* sink, int sm_count, int iters, cudaStream_t st);
 // ks_kernel.cu
 void launch_keyswitch(const uint64_t* ksk, const uint64_t* in_big, uint64_t* out_small, int count, int big_dim,
                       int n, int base_log, int level, cudaStream_t st);
+
+// linear_kernels.cu: out[dst(b)] = sum_t coef[t] * pool[slot[t]] + cst[b] * delta on the body
+void launch_lincomb(const uint64_t* pool, const int32_t* row_ptr, const int32_t* slot, const int32_t* coef,
+                    const int32_t* cst, uint64_t delta, uint64_t* out, const int32_t* dst_idx, int count, int words,
+                    cudaStream_t st);
 
 }  // namespace fsc

@@ -89,7 +89,7 @@ template <typename AccT>
 __global__ void __launch_bounds__(64, 4) pbs_pair_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                        int n, int base_log, const uint64_t* __restrict__ luts,
                                                        const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
-                                                       int count) {
+                                                       const int32_t* __restrict__ out_idx, int count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int p = threadIdx.x >> 5;
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(64, 4) pbs_pair_kernel(const cplx* __restrict_
     }
     __syncthreads();
 
-    uint64_t* out = out_big + (size_t)c * (kN + 1);
+    uint64_t* out = out_big + (size_t)(out_idx ? out_idx[c] : c) * (kN + 1);
     for (int j = threadIdx.x; j <= kN; j += 64) out[j] = extract_word<AccT>(acc_all, acc_all + 1024, j);
 }
 
@@ -209,7 +209,7 @@ template <typename AccT, int CTS, int NCH>
 __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                                      int n, int base_log, const uint64_t* __restrict__ luts,
                                                                      const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
-                                                                     int count) {
+                                                                     const int32_t* __restrict__ out_idx, int count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pair_t<AccT>* acc_all = reinterpret_cast<pair_t<AccT>*>(smem_raw);
     cplx* xbuf_all = reinterpret_cast<cplx*>(smem_raw + (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>));
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
     pair_barrier(1 + ctl);
 
     if (live) {
-        uint64_t* out = out_big + (size_t)c * (kN + 1);
+        uint64_t* out = out_big + (size_t)(out_idx ? out_idx[c] : c) * (kN + 1);
         const pair_t<AccT>* mask = acc_all + (size_t)(ctl * 2) * 1024;
         for (int j = (p * 32 + lane); j <= kN; j += 64) out[j] = extract_word<AccT>(mask, mask + 1024, j);
     }
@@ -356,7 +356,7 @@ void launch_bsk_convert(const uint64_t* bsk, void* out, int n, cudaStream_t st) 
 
 template <typename AccT>
 static void launch_pbs_pair_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
-                              const uint32_t* lut_idx, uint64_t* out_big, int count, cudaStream_t st) {
+                              const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     const size_t smem = 2 * 1024 * sizeof(pair_t<AccT>) + 2 * 1024 * sizeof(cplx);
     static bool configured = false;
     if (!configured) {
@@ -364,12 +364,12 @@ static void launch_pbs_pair_t(const void* bsk_f, const uint64_t* in_small, int n
         configured = true;
     }
     pbs_pair_kernel<AccT><<<count, 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts,
-                                                    lut_idx, out_big, count);
+                                                    lut_idx, out_big, out_idx, count);
 }
 
 template <typename AccT, int CTS, int NCH>
 static void launch_pbs_ring_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
-                              const uint32_t* lut_idx, uint64_t* out_big, int count, cudaStream_t st) {
+                              const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     const size_t smem = (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>) + (size_t)CTS * 2 * 1024 * sizeof(cplx) +
                         (size_t)NCH * kChunkCplx * sizeof(cplx) + 2 * NCH * sizeof(uint64_t);
     static bool configured = false;
@@ -379,7 +379,7 @@ static void launch_pbs_ring_t(const void* bsk_f, const uint64_t* in_small, int n
     }
     const int grid = (count + CTS - 1) / CTS;
     pbs_ring_kernel<AccT, CTS, NCH><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log,
-                                                                        luts, lut_idx, out_big, count);
+                                                                        luts, lut_idx, out_big, out_idx, count);
 }
 
 static int pbs_variant() {
@@ -392,14 +392,14 @@ static int pbs_variant() {
 }
 
 void launch_pbs(int acc_bits, const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
-                const uint32_t* lut_idx, uint64_t* out_big, int count, cudaStream_t st) {
+                const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     if (count <= 0) return;
     if (pbs_variant() == 0) {
-        if (acc_bits == 32) launch_pbs_pair_t<uint32_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, count, st);
-        else launch_pbs_pair_t<uint64_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, count, st);
+        if (acc_bits == 32) launch_pbs_pair_t<uint32_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
+        else launch_pbs_pair_t<uint64_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
     } else {
-        if (acc_bits == 32) launch_pbs_ring_t<uint32_t, 4, 4>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, count, st);
-        else launch_pbs_ring_t<uint64_t, 3, 4>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, count, st);
+        if (acc_bits == 32) launch_pbs_ring_t<uint32_t, 4, 4>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
+        else launch_pbs_ring_t<uint64_t, 3, 4>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
     }
 }
 

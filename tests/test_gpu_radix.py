@@ -1,0 +1,99 @@
+"""Radix operators on the GPU with real encryptions (keys and client side from the oracle), checked
+against the plaintext contract of the reference's operators and its known answers."""
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PRESET = "2_2_gaussian"
+
+
+class Client:
+    """client side of the reference (FheUintN::try_encrypt / decrypt, src/biguint.rs:26,70), on the oracle"""
+
+    def __init__(self, K, api):
+        self.K, self.api, self.stream = K, api, 0
+
+    def enc(self, value, n_blocks):
+        digits = np.array([(int(value) >> (2 * i)) & 3 for i in range(n_blocks)], dtype=np.uint64)
+        ct = self.K.encrypt_msgs(digits, seed=99, stream=self.stream)
+        self.stream += n_blocks
+        return self.api.from_lwe(ct)
+
+    def dec(self, r):
+        d = self.K.decrypt_msgs(self.api.to_lwe(r))
+        assert (d < 4).all(), d
+        return sum(int(v) << (2 * i) for i, v in enumerate(d))
+
+
+@pytest.fixture(scope="module")
+def cl(gpu_ctx, oracle_keys):
+    ctx = gpu_ctx(PRESET, 64)
+    return Client(oracle_keys(PRESET), ctx.radix)
+
+
+def test_u32_add_mul_kats(cl):
+    F = 0xFFFFFFFF
+    a, b = cl.enc(F, 16), cl.enc(1, 16)
+    assert cl.dec(a + b) == 0                                    # src/biguint.rs:469-499 wrapping
+    assert cl.dec(cl.enc(123, 16) * 456) == 56088                # src/schnorr.rs:575-592
+    assert cl.dec(cl.enc(123, 16) + 456) == 579                  # src/schnorr.rs:595-607
+    x, y = 123456789, 987654321
+    assert cl.dec(cl.enc(x, 16) * cl.enc(y, 16)) == (x * y) & F
+    assert cl.dec(cl.enc(x, 16) + cl.enc(y, 16)) == (x + y) & F
+    assert cl.dec(cl.enc(x, 16) - cl.enc(y, 16)) == (x - y) & F
+
+
+def test_u64_carry_extraction_kats(cl):
+    """src/biguint.rs:429-466 and :502-527: extract_upper_bits / extract_lower_bits of FheUint64 sums."""
+    F = 0xFFFFFFFF
+    api = cl.api
+    a64 = lambda v: api.cast(cl.enc(v, 16), 32)
+    for x, y, hi, lo in ((5, 3, 0, 8), (F, 1, 1, 0), (F, F, 1, 0xFFFFFFFE)):
+        s = a64(x) + a64(y)
+        assert cl.dec(api.cast(s >> 32, 16)) == hi and cl.dec(api.cast(s & F, 16)) == lo
+    p = a64(F) * a64(2)
+    assert cl.dec(p >> 32) == 1 and cl.dec(p & F) == 0xFFFFFFFE
+    p = a64(F) * a64(F)
+    assert cl.dec(p) == F * F
+
+
+def test_perf_test_chain(cl):
+    """src/perf_test.rs:14-75 on its own operands."""
+    api = cl.api
+    a, b, c = cl.enc(1344, 16), cl.enc(5, 16), cl.enc(7, 4)
+    assert cl.dec(a + b) == 1349
+    assert cl.dec(a * b) == 6720
+    sh = a >> b
+    assert cl.dec(sh) == 42
+    mn = api.min(api.cast(sh, 4), c)
+    assert cl.dec(mn) == 7
+    assert cl.dec(mn & 1) == 1
+    assert cl.dec(a // 5) == 268
+
+
+def test_random_ops_u32(cl):
+    rnd = random.Random(11)
+    F = 0xFFFFFFFF
+    for _ in range(3):
+        x, y = rnd.getrandbits(32), rnd.getrandbits(32)
+        a, b = cl.enc(x, 16), cl.enc(y, 16)
+        assert cl.dec(a * b) == (x * y) & F
+        assert cl.dec(cl.api.min(a, b)) == min(x, y)
+        assert cl.dec(a >> (y % 32)) == x >> (y % 32)
+        assert cl.dec(a >> b) == x >> (y % 32)
+        assert cl.dec(a & b) == x & y
+        d = rnd.getrandbits(20) | 1
+        assert cl.dec(a // d) == x // d and cl.dec(a % d) == x % d
+
+
+def test_256_bit_mul_add(cl):
+    """BASELINE configs[2]: one 256 x 256 -> 512-bit product + 256-bit addend (the k + e*d of signing)."""
+    rnd = random.Random(12)
+    x, y, z = rnd.getrandbits(256), rnd.getrandbits(256), rnd.getrandbits(256)
+    a, b, c = cl.enc(x, 128), cl.enc(y, 128), cl.enc(z, 128)
+    prod = cl.api.mul_wide(a, b, 256)
+    s = cl.api.sum([prod, cl.api.cast(c, 257)], 257)
+    assert cl.dec(s) == x * y + z
