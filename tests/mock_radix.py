@@ -24,6 +24,10 @@ class MockRadix:
         self.ctx = h
         self.api = RadixApi(self.L, h, self._check)
 
+    @property
+    def radix(self):
+        return self.api
+
     def _check(self, rc):
         if rc != 0:
             raise RuntimeError("radix error %d: %s" % (rc, self.L.fscmock_last_error(self.ctx).decode()))
@@ -48,3 +52,16 @@ class MockRadix:
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self.L.fscmock_counters(self.ctx, C.byref(a), C.byref(b), C.byref(c))
         return dict(violations=a.value, live_slots=b.value, max_batch=c.value)
+
+
+class MockClientKey:
+    """ClientKey stand-in for the mock backend: 'encrypts' u32 digits as trivial LWE blocks."""
+
+    def __init__(self, mock):
+        self.m = mock
+
+    def encrypt_u32(self, value, api):
+        return self.m.enc(value, 16)
+
+    def decrypt(self, r, api):
+        return self.m.dec(r)
