@@ -22,6 +22,10 @@ struct Engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     void* bsk_f = nullptr;          // Fourier bootstrapping key [n][32 r][4 g][32 lane] complex f64
     uint64_t* ksk = nullptr;        // [kN][l_ks][n+1]
+    uint8_t* ksk_limbs = nullptr;   // byte-limb transpose of the KSK for the tensor-core keyswitch [8(n+1) padded][kN*l_ks]
+    int8_t* ks_digits = nullptr;    // digit matrix of the current batch [rows padded to 128][kN*l_ks]
+    size_t ks_digits_cap = 0;
+    int ks_variant = 1;             // 0 = CUDA-core kernel, 1 = tensor-core (mma.sync s8 x u8) kernel
     uint64_t* scratch_small = nullptr;   // keyswitch outputs of the current batch
     uint32_t* scratch_idx = nullptr;     // LUT indices of the current batch
     size_t scratch_cap = 0;

@@ -1,6 +1,7 @@
 // fsc_api.cu — context, device buffers and the C ABI of include/fhe_sign_cuda.h.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -54,6 +55,8 @@ Engine::Engine(const fsc_params& prm, int device, uintptr_t ext_stream) : p(prm)
     FSC_CUDA_CHECK(cudaEventCreate(&ev0));
     FSC_CUDA_CHECK(cudaEventCreate(&ev1));
     pbs_init_constants();
+    const char* kv = getenv("FSC_KS_VARIANT");      // "simt" | "mma" (default)
+    ks_variant = (kv && kv[0] == 's') ? 0 : 1;
 }
 
 Engine::~Engine() {
@@ -61,6 +64,8 @@ Engine::~Engine() {
     cudaStreamSynchronize(stream);
     if (bsk_f) cudaFree(bsk_f);
     if (ksk) cudaFree(ksk);
+    if (ksk_limbs) cudaFree(ksk_limbs);
+    if (ks_digits) cudaFree(ks_digits);
     if (scratch_small) cudaFree(scratch_small);
     if (scratch_idx) cudaFree(scratch_idx);
     if (scratch_big) cudaFree(scratch_big);
@@ -81,6 +86,7 @@ void Engine::upload_keys(const uint64_t* bsk_std, size_t bsk_words, const uint64
     FSC_REQUIRE(ksk_words == want_ksk, "keyswitching key size does not match the parameter set");
     if (bsk_f) { cudaFree(bsk_f); bsk_f = nullptr; }
     if (ksk) { cudaFree(ksk); ksk = nullptr; }
+    if (ksk_limbs) { cudaFree(ksk_limbs); ksk_limbs = nullptr; }
     uint64_t* tmp = nullptr;
     FSC_CUDA_CHECK(cudaMalloc(&tmp, want_bsk * 8));
     cudaError_t e = cudaMalloc(&bsk_f, n * 32 * 4 * 32 * 16);
@@ -91,6 +97,13 @@ void Engine::upload_keys(const uint64_t* bsk_std, size_t bsk_words, const uint64
     FSC_CUDA_CHECK(cudaMemcpyAsync(ksk, ksk_h, want_ksk * 8, cudaMemcpyHostToDevice, stream));
     launch_bsk_convert(tmp, bsk_f, (int)n, stream); ++launches;
     FSC_CUDA_CHECK(cudaGetLastError());
+    {
+        const size_t K = (size_t)N * p.ks_level;
+        e = cudaMalloc(&ksk_limbs, ks_mma_limb_rows((int)n) * K);
+        if (e != cudaSuccess) { cudaFree(tmp); FSC_CUDA_CHECK(e); }
+        launch_ksk_limb_transpose(ksk, ksk_limbs, (int)K, (int)n, stream); ++launches;
+        FSC_CUDA_CHECK(cudaGetLastError());
+    }
     FSC_CUDA_CHECK(cudaStreamSynchronize(stream));
     cudaFree(tmp);
 }
@@ -136,9 +149,23 @@ const uint32_t* Engine::stage_lut_idx(const uint32_t* lut_idx, size_t count, con
 void Engine::keyswitch(const uint64_t* in_big, uint64_t* out_small, size_t count) {
     use();
     if (!ksk) throw Error(FSC_ERR_NO_KEYS, "server keys not uploaded");
-    launch_keyswitch(ksk, in_big, out_small, (int)count, (int)p.poly_size, (int)p.lwe_dim, (int)p.ks_base_log,
-                     (int)p.ks_level, stream);
-    ++launches;
+    if (ks_variant == 1) {
+        const size_t rows = ks_mma_digit_rows(count), K = (size_t)p.poly_size * p.ks_level;
+        if (rows > ks_digits_cap) {
+            FSC_CUDA_CHECK(cudaStreamSynchronize(stream));
+            if (ks_digits) cudaFree(ks_digits);
+            ks_digits = nullptr; ks_digits_cap = 0;
+            FSC_CUDA_CHECK(cudaMalloc(&ks_digits, rows * K));
+            ks_digits_cap = rows;
+        }
+        launch_keyswitch_mma(ksk_limbs, ks_digits, in_big, out_small, (int)count, (int)p.poly_size, (int)p.lwe_dim,
+                             (int)p.ks_base_log, (int)p.ks_level, stream);
+        launches += 2;
+    } else {
+        launch_keyswitch(ksk, in_big, out_small, (int)count, (int)p.poly_size, (int)p.lwe_dim, (int)p.ks_base_log,
+                         (int)p.ks_level, stream);
+        ++launches;
+    }
     FSC_CUDA_CHECK(cudaGetLastError());
 }
 

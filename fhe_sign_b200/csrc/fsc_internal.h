@@ -41,6 +41,13 @@ double launch_fp64_peak(double* sink, int sm_count, int iters, cudaStream_t st);
 void launch_keyswitch(const uint64_t* ksk, const uint64_t* in_big, uint64_t* out_small, int count, int big_dim,
                       int n, int base_log, int level, cudaStream_t st);
 
+// ks_mma_kernel.cu (tensor-core keyswitch)
+size_t ks_mma_limb_rows(int n);
+size_t ks_mma_digit_rows(size_t count);
+void launch_ksk_limb_transpose(const uint64_t* ksk, uint8_t* out, int K, int n, cudaStream_t st);
+void launch_keyswitch_mma(const uint8_t* limbs, int8_t* digits, const uint64_t* in_big, uint64_t* out_small, int count,
+                          int big_dim, int n, int base_log, int level, cudaStream_t st);
+
 // linear_kernels.cu: out[dst(b)] = sum_t coef[t] * pool[slot[t]] + cst[b] * delta on the body
 void launch_lincomb(const uint64_t* pool, const int32_t* row_ptr, const int32_t* slot, const int32_t* coef,
                     const int32_t* cst, uint64_t delta, uint64_t* out, const int32_t* dst_idx, int count, int words,

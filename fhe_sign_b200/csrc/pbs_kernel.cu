@@ -31,22 +31,35 @@ void pbs_init_constants() {
 }
 
 // forward negacyclic FFT of the 32 x 32 complex points held by the warp (v[j2] at lane j1)
-__device__ __forceinline__ void warp_fft_fwd(int lane, cplx* xbuf, const cplx (&s2)[16], cplx (&v)[32]) {
+template <class C2>
+__device__ __forceinline__ void warp_fft_fwd_c(int lane, cplx* xbuf, const C2& c2, cplx (&v)[32]) {
     dft32_fwd(v, S1Dev());
     xpose_store_fwd(lane, xbuf, v);
     __syncwarp();
     xpose_load_fwd(lane, xbuf, v);
     __syncwarp();
-    dft32_fwd(v, RegConsts(s2));
+    dft32_fwd(v, c2);
 }
-__device__ __forceinline__ void warp_fft_inv(int lane, cplx* xbuf, const cplx (&s2)[16], cplx (&v)[32]) {
-    dft32_inv(v, RegConsts(s2));
+template <class C2>
+__device__ __forceinline__ void warp_fft_inv_c(int lane, cplx* xbuf, const C2& c2, cplx (&v)[32]) {
+    dft32_inv(v, c2);
     xpose_store_inv(lane, xbuf, v);
     __syncwarp();
     xpose_load_inv(lane, xbuf, v);
     __syncwarp();
     dft32_inv(v, S1Dev());
 }
+__device__ __forceinline__ void warp_fft_fwd(int lane, cplx* xbuf, const cplx (&s2)[16], cplx (&v)[32]) {
+    warp_fft_fwd_c(lane, xbuf, RegConsts(s2), v);
+}
+__device__ __forceinline__ void warp_fft_inv(int lane, cplx* xbuf, const cplx (&s2)[16], cplx (&v)[32]) {
+    warp_fft_inv_c(lane, xbuf, RegConsts(s2), v);
+}
+// per-lane pass-2 constants kept in a shared-memory table [16][32] instead of 32 registers
+struct SmemLaneConsts {
+    const cplx* t;      // already offset by lane
+    __device__ __forceinline__ cplx get(int ci) const { return t[ci * 32]; }
+};
 
 __device__ __forceinline__ cplx ldg_cplx(const cplx* p) {
     const double2 d = __ldg(reinterpret_cast<const double2*>(p));
@@ -205,7 +218,7 @@ __device__ __forceinline__ void pair_barrier(int id) {      // the two warps of 
     asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
 
-template <typename AccT, int CTS, int NCH>
+template <typename AccT, int CTS, int NCH, bool S2S>
 __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                                      int n, int base_log, const uint64_t* __restrict__ luts,
                                                                      const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
@@ -214,7 +227,8 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
     pair_t<AccT>* acc_all = reinterpret_cast<pair_t<AccT>*>(smem_raw);
     cplx* xbuf_all = reinterpret_cast<cplx*>(smem_raw + (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>));
     cplx* ring = xbuf_all + (size_t)CTS * 2 * 1024;
-    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)NCH * kChunkCplx);
+    cplx* s2tab = ring + (size_t)NCH * kChunkCplx;
+    uint64_t* full = reinterpret_cast<uint64_t*>(s2tab + (S2S ? 16 * 32 : 0));
     uint64_t* empty = full + NCH;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -244,8 +258,19 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
     const uint64_t* ct = in_small + (size_t)c * (n + 1);
     const uint64_t* lut = luts + (size_t)(lut_idx ? lut_idx[c] : 0) * kN;
 
-    cplx s2[16];
-    lane_consts(4 * lane + 1, s2);
+    cplx s2[S2S ? 1 : 16];
+    if (S2S) {
+        if (warp == 0) {
+            cplx tmp[16];
+            lane_consts(4 * lane + 1, tmp);
+#pragma unroll
+            for (int ci = 0; ci < 16; ++ci) s2tab[ci * 32 + lane] = tmp[ci];
+        }
+        __syncthreads();
+    } else {
+        lane_consts(4 * lane + 1, reinterpret_cast<cplx(&)[16]>(s2));
+    }
+    const SmemLaneConsts c2s{s2tab + lane};
     {
         const int b = modswitch(ct[n]);
 #pragma unroll 4
@@ -257,6 +282,8 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
     }
     __syncwarp();
 
+    // Fourier-domain product of this warp: X_p <- X_p * G[p][p] + X_{1-p} * G[1-p][p]  (g = 2 row + col)
+    const int g_own = 3 * p, g_oth = 2 - p;
     int a_chunk = 0;
     int t = 0;                                          // ring chunk counter
     for (int i = 0; i < n; ++i) {
@@ -266,7 +293,8 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
 
         cplx X[32];
         cmux_head<AccT>(lane, acc, a, base_log, X);
-        warp_fft_fwd(lane, xbuf, s2, X);
+        if (S2S) warp_fft_fwd_c(lane, xbuf, c2s, X);
+        else warp_fft_fwd(lane, xbuf, reinterpret_cast<cplx(&)[16]>(s2), X);
 #pragma unroll
         for (int r = 0; r < 32; ++r) xbuf[r * 32 + lane] = X[r];
         pair_barrier(1 + ctl);
@@ -275,16 +303,15 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
         for (int k = 0; k < kChunksPerStep; ++k, ++t) {
             const int stage = t % NCH;
             mbar_wait(full + stage, (uint32_t)(t / NCH) & 1);
-            const cplx* g = ring + (size_t)stage * kChunkCplx + lane + p * 32;
+            const cplx* g = ring + (size_t)stage * kChunkCplx + lane;
 #pragma unroll
             for (int rr = 0; rr < kChunkSlots; ++rr) {
                 const int r = k * kChunkSlots + rr;
                 const cplx o = xother[r * 32 + lane];
-                const cplx g0 = g[(rr * 4) * 32], g1 = g[(rr * 4 + 2) * 32];      // G[0][p], G[1][p]
-                const cplx x0 = p ? o : X[r];
-                const cplx x1 = p ? X[r] : o;
-                X[r].x = x0.x * g0.x - x0.y * g0.y + x1.x * g1.x - x1.y * g1.y;
-                X[r].y = x0.x * g0.y + x0.y * g0.x + x1.x * g1.y + x1.y * g1.x;
+                const cplx gw = g[(rr * 4 + g_own) * 32], go = g[(rr * 4 + g_oth) * 32];
+                const cplx x = X[r];
+                X[r].x = x.x * gw.x - x.y * gw.y + o.x * go.x - o.y * go.y;
+                X[r].y = x.x * gw.y + x.y * gw.x + o.x * go.y + o.y * go.x;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + stage);
@@ -301,7 +328,8 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
         }
         pair_barrier(1 + ctl);
 
-        warp_fft_inv(lane, xbuf, s2, X);
+        if (S2S) warp_fft_inv_c(lane, xbuf, c2s, X);
+        else warp_fft_inv(lane, xbuf, reinterpret_cast<cplx(&)[16]>(s2), X);
         cmux_tail<AccT>(lane, acc, X);
         __syncwarp();
     }
@@ -367,26 +395,26 @@ static void launch_pbs_pair_t(const void* bsk_f, const uint64_t* in_small, int n
                                                     lut_idx, out_big, out_idx, count);
 }
 
-template <typename AccT, int CTS, int NCH>
+template <typename AccT, int CTS, int NCH, bool S2S>
 static void launch_pbs_ring_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
                               const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     const size_t smem = (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>) + (size_t)CTS * 2 * 1024 * sizeof(cplx) +
-                        (size_t)NCH * kChunkCplx * sizeof(cplx) + 2 * NCH * sizeof(uint64_t);
+                        (size_t)NCH * kChunkCplx * sizeof(cplx) + (S2S ? 16 * 32 * sizeof(cplx) : 0) + 2 * NCH * sizeof(uint64_t);
     static bool configured = false;
     if (!configured) {
-        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_ring_kernel<AccT, CTS, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_ring_kernel<AccT, CTS, NCH, S2S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     const int grid = (count + CTS - 1) / CTS;
-    pbs_ring_kernel<AccT, CTS, NCH><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log,
+    pbs_ring_kernel<AccT, CTS, NCH, S2S><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log,
                                                                         luts, lut_idx, out_big, out_idx, count);
 }
 
 static int pbs_variant() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("FSC_PBS_VARIANT");      // "pair" | "ring" (default)
-        v = (e && e[0] == 'p') ? 0 : 1;
+        const char* e = getenv("FSC_PBS_VARIANT");      // "pair" | "ring" | "s2smem" (default)
+        v = (e && e[0] == 'p') ? 0 : (e && e[0] == 'r') ? 1 : 2;
     }
     return v;
 }
@@ -397,9 +425,12 @@ void launch_pbs(int acc_bits, const void* bsk_f, const uint64_t* in_small, int n
     if (pbs_variant() == 0) {
         if (acc_bits == 32) launch_pbs_pair_t<uint32_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
         else launch_pbs_pair_t<uint64_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
+    } else if (pbs_variant() == 2) {
+        if (acc_bits == 32) launch_pbs_ring_t<uint32_t, 4, 3, true>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
+        else launch_pbs_ring_t<uint64_t, 3, 3, true>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
     } else {
-        if (acc_bits == 32) launch_pbs_ring_t<uint32_t, 4, 4>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
-        else launch_pbs_ring_t<uint64_t, 3, 4>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
+        if (acc_bits == 32) launch_pbs_ring_t<uint32_t, 4, 4, false>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
+        else launch_pbs_ring_t<uint64_t, 3, 4, false>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
     }
 }
 

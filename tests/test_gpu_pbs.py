@@ -39,6 +39,25 @@ def test_keyswitch_bit_exact(gpu_ctx, oracle_keys, rng, preset, count):
     din.free(); dout.free()
 
 
+@pytest.mark.parametrize("variant", ["simt", "mma"])
+def test_keyswitch_variants_bit_exact(oracle_keys, rng, variant, monkeypatch):
+    """both keyswitch kernels (CUDA-core and int8 tensor-core limb GEMM) against the oracle, ragged counts."""
+    import fhe_sign_b200 as fsb
+    from fhe_sign_b200.capi import LWE_BIG, LWE_SMALL
+    monkeypatch.setenv("FSC_KS_VARIANT", variant)
+    K = oracle_keys("2_2_gaussian")
+    ctx = fsb.Context(fsb.Params.preset("2_2_gaussian"))
+    ctx.upload_keys(K.bsk, K.ksk)
+    for count in (1, 129, 300):
+        ct = rng.integers(0, 2**64, (count, 2049), dtype=np.uint64)        # arbitrary words: keyswitch is linear integer work
+        ct[0, :6] = [0, 2**64 - 1, 2**63, 2**48, 2**48 - 1, 3 << 47]
+        din, dout = ctx.lwe(LWE_BIG, count).upload(ct), ctx.lwe(LWE_SMALL, count)
+        ctx.keyswitch(din, dout)
+        assert np.array_equal(dout.download(), K.keyswitch(ct)), (variant, count)
+        din.free(); dout.free()
+    ctx.close()
+
+
 @pytest.mark.parametrize("acc_bits", [64, 32])
 @pytest.mark.parametrize("preset", ["toy", "2_2_gaussian", "2_2_tuniform"])
 def test_pbs_all_messages_all_luts(gpu_ctx, oracle_keys, rng, preset, acc_bits):
