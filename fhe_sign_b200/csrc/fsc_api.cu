@@ -174,7 +174,7 @@ void Engine::pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut
     use();
     if (!bsk_f) throw Error(FSC_ERR_NO_KEYS, "server keys not uploaded");
     launch_pbs((int)p.acc_bits, bsk_f, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, out_big,
-               out_idx_dev, (int)count, stream);
+               out_idx_dev, (int)count, sm_count, stream);
     ++launches;
     FSC_CUDA_CHECK(cudaGetLastError());
 }

@@ -18,42 +18,62 @@
 
 namespace fsc {
 
-__constant__ cplx c_s1[16];     // uniform pass-1 node constants (g = 32)
+__constant__ cplx c_uni[kUniSize];     // uniform constants (pbs_core.cuh fill_uniform_table)
 
 struct S1Dev {
-    __device__ __forceinline__ cplx get(int ci) const { return c_s1[ci]; }
+    __device__ __forceinline__ cplx get(int ci) const { return c_uni[ci]; }
 };
 
 void pbs_init_constants() {
-    cplx h[16];
-    lane_consts(32, h);
-    FSC_CUDA_CHECK(cudaMemcpyToSymbol(c_s1, h, sizeof(h)));
+    cplx h[kUniSize];
+    fill_uniform_table(h);
+    FSC_CUDA_CHECK(cudaMemcpyToSymbol(c_uni, h, sizeof(h)));
 }
 
 // forward negacyclic FFT of the 32 x 32 complex points held by the warp (v[j2] at lane j1)
-template <class C2>
+struct S1PlainDev {
+    __device__ __forceinline__ cplx get(int ci) const { return c_uni[kUniPlainP1 + ci]; }
+};
+// FFT formulation switches (bit 0: tangent-form forward pass 1, bit 1: tangent-form forward pass 2 levels 3..5,
+// bit 2: inverse pass 1 as DIT + fused untwist/scale).  FV selects what the blind-rotation kernels use.
+template <int FV> struct fft_opts {
+    static constexpr bool f1 = FV & 1, f2 = (FV >> 1) & 1, i1 = (FV >> 2) & 1;
+    static constexpr int p2_min_level = f2 ? kP2MinLevel : 6;      // 6: per-lane table stays (re, im)
+};
+// c2: the 16 per-lane pass-2 constants (lane_consts_tan with kP2Center / fft_opts<FV>::p2_min_level)
+template <int FV, class C2>
 __device__ __forceinline__ void warp_fft_fwd_c(int lane, cplx* xbuf, const C2& c2, cplx (&v)[32]) {
-    dft32_fwd(v, S1Dev());
+    if (fft_opts<FV>::f1) dft32_fwd_tan<kP1Center, kP1MinLevel>(v, S1Dev());
+    else dft32_fwd(v, S1PlainDev());
     xpose_store_fwd(lane, xbuf, v);
     __syncwarp();
     xpose_load_fwd(lane, xbuf, v);
     __syncwarp();
-    dft32_fwd(v, c2);
+    dft32_fwd_tan<kP2Center, fft_opts<FV>::p2_min_level>(v, c2);
 }
-template <class C2>
+// with fft_opts<FV>::i1 the result is already scaled (TW_BASE table); otherwise the tail scales
+template <int FV, int TW_BASE, class C2>
 __device__ __forceinline__ void warp_fft_inv_c(int lane, cplx* xbuf, const C2& c2, cplx (&v)[32]) {
-    dft32_inv(v, c2);
+    dft32_inv_tan<kP2Center, fft_opts<FV>::p2_min_level>(v, c2);
     xpose_store_inv(lane, xbuf, v);
     __syncwarp();
     xpose_load_inv(lane, xbuf, v);
     __syncwarp();
-    dft32_inv(v, S1Dev());
+    if (fft_opts<FV>::i1) idft32_dit_twist(v, S1Dev(), TW_BASE);
+    else dft32_inv(v, S1PlainDev());
 }
+template <int FV, typename AccT>
+__device__ __forceinline__ void tail_fv(int lane, pair_t<AccT>* acc, const cplx (&v)[32]) {
+    if (fft_opts<FV>::i1) cmux_tail_scaled<AccT>(lane, acc, v);
+    else cmux_tail<AccT>(lane, acc, v);
+}
+constexpr int kDefaultFV = 0;
 __device__ __forceinline__ void warp_fft_fwd(int lane, cplx* xbuf, const cplx (&s2)[16], cplx (&v)[32]) {
-    warp_fft_fwd_c(lane, xbuf, RegConsts(s2), v);
+    warp_fft_fwd_c<kDefaultFV>(lane, xbuf, RegConsts(s2), v);
 }
+template <int TW_BASE>
 __device__ __forceinline__ void warp_fft_inv(int lane, cplx* xbuf, const cplx (&s2)[16], cplx (&v)[32]) {
-    warp_fft_inv_c(lane, xbuf, RegConsts(s2), v);
+    warp_fft_inv_c<kDefaultFV, TW_BASE>(lane, xbuf, RegConsts(s2), v);
 }
 // per-lane pass-2 constants kept in a shared-memory table [16][32] instead of 32 registers
 struct SmemLaneConsts {
@@ -77,7 +97,7 @@ __global__ void __launch_bounds__(32) bsk_convert_kernel(const uint64_t* __restr
     const int i = blockIdx.x >> 2, g = blockIdx.x & 3;
     const uint64_t* src = bsk + (size_t)blockIdx.x * kN;
     cplx s2[16];
-    lane_consts(4 * lane + 1, s2);
+    lane_consts_tan(4 * lane + 1, kP2Center, fft_opts<kDefaultFV>::p2_min_level, s2);
     cplx v[32];
 #pragma unroll
     for (int j2 = 0; j2 < 32; ++j2) {
@@ -117,7 +137,7 @@ __global__ void __launch_bounds__(64, 4) pbs_pair_kernel(const cplx* __restrict_
     const uint64_t* lut = luts + (size_t)(lut_idx ? lut_idx[c] : 0) * kN;
 
     cplx s2[16];
-    lane_consts(4 * lane + 1, s2);
+    lane_consts_tan(4 * lane + 1, kP2Center, fft_opts<kDefaultFV>::p2_min_level, s2);
 
     // accumulator <- (0, X^{-b} * LUT)
     {
@@ -166,8 +186,8 @@ __global__ void __launch_bounds__(64, 4) pbs_pair_kernel(const cplx* __restrict_
         }
         __syncthreads();
 
-        warp_fft_inv(lane, xbuf, s2, X);
-        cmux_tail<AccT>(lane, acc, X);
+        warp_fft_inv<uni_tw<AccT>::base>(lane, xbuf, s2, X);
+        tail_fv<kDefaultFV, AccT>(lane, acc, X);
         __syncwarp();
     }
     __syncthreads();
@@ -218,7 +238,7 @@ __device__ __forceinline__ void pair_barrier(int id) {      // the two warps of 
     asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
 
-template <typename AccT, int CTS, int NCH, bool S2S>
+template <typename AccT, int CTS, int NCH, bool S2S, int FV>
 __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                                      int n, int base_log, const uint64_t* __restrict__ luts,
                                                                      const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
@@ -262,13 +282,13 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
     if (S2S) {
         if (warp == 0) {
             cplx tmp[16];
-            lane_consts(4 * lane + 1, tmp);
+            lane_consts_tan(4 * lane + 1, kP2Center, fft_opts<FV>::p2_min_level, tmp);
 #pragma unroll
             for (int ci = 0; ci < 16; ++ci) s2tab[ci * 32 + lane] = tmp[ci];
         }
         __syncthreads();
     } else {
-        lane_consts(4 * lane + 1, reinterpret_cast<cplx(&)[16]>(s2));
+        lane_consts_tan(4 * lane + 1, kP2Center, fft_opts<FV>::p2_min_level, reinterpret_cast<cplx(&)[16]>(s2));
     }
     const SmemLaneConsts c2s{s2tab + lane};
     {
@@ -293,8 +313,8 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
 
         cplx X[32];
         cmux_head<AccT>(lane, acc, a, base_log, X);
-        if (S2S) warp_fft_fwd_c(lane, xbuf, c2s, X);
-        else warp_fft_fwd(lane, xbuf, reinterpret_cast<cplx(&)[16]>(s2), X);
+        if (S2S) warp_fft_fwd_c<FV>(lane, xbuf, c2s, X);
+        else warp_fft_fwd_c<FV>(lane, xbuf, RegConsts(reinterpret_cast<cplx(&)[16]>(s2)), X);
 #pragma unroll
         for (int r = 0; r < 32; ++r) xbuf[r * 32 + lane] = X[r];
         pair_barrier(1 + ctl);
@@ -328,9 +348,9 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
         }
         pair_barrier(1 + ctl);
 
-        if (S2S) warp_fft_inv_c(lane, xbuf, c2s, X);
-        else warp_fft_inv(lane, xbuf, reinterpret_cast<cplx(&)[16]>(s2), X);
-        cmux_tail<AccT>(lane, acc, X);
+        if (S2S) warp_fft_inv_c<FV, uni_tw<AccT>::base>(lane, xbuf, c2s, X);
+        else warp_fft_inv_c<FV, uni_tw<AccT>::base>(lane, xbuf, RegConsts(reinterpret_cast<cplx(&)[16]>(s2)), X);
+        tail_fv<FV, AccT>(lane, acc, X);
         __syncwarp();
     }
     pair_barrier(1 + ctl);
@@ -351,7 +371,7 @@ __global__ void __launch_bounds__(32) negacyclic_mul_kernel(const uint64_t* __re
     const int lane = threadIdx.x;
     a += (size_t)blockIdx.x * kN; b += (size_t)blockIdx.x * kN; c += (size_t)blockIdx.x * kN;
     cplx s2[16];
-    lane_consts(4 * lane + 1, s2);
+    lane_consts_tan(4 * lane + 1, kP2Center, fft_opts<kDefaultFV>::p2_min_level, s2);
     cplx va[32], vb[32];
 #pragma unroll
     for (int j2 = 0; j2 < 32; ++j2) {
@@ -367,11 +387,11 @@ __global__ void __launch_bounds__(32) negacyclic_mul_kernel(const uint64_t* __re
         va[r].x = x.x * y.x - x.y * y.y; va[r].y = x.x * y.y + x.y * y.x;
     }
     __syncwarp();
-    warp_fft_inv(lane, xbuf, s2, va);
+    warp_fft_inv<kUniTw64>(lane, xbuf, s2, va);
 #pragma unroll
     for (int j2 = 0; j2 < 32; ++j2) {
-        c[lane + 32 * j2] = to_acc<uint64_t>(va[j2].x);
-        c[lane + 32 * j2 + 1024] = to_acc<uint64_t>(va[j2].y);
+        c[lane + 32 * j2] = fft_opts<kDefaultFV>::i1 ? to_acc_scaled<uint64_t>(va[j2].x) : to_acc<uint64_t>(va[j2].x);
+        c[lane + 32 * j2 + 1024] = fft_opts<kDefaultFV>::i1 ? to_acc_scaled<uint64_t>(va[j2].y) : to_acc<uint64_t>(va[j2].y);
     }
 }
 
@@ -395,43 +415,52 @@ static void launch_pbs_pair_t(const void* bsk_f, const uint64_t* in_small, int n
                                                     lut_idx, out_big, out_idx, count);
 }
 
-template <typename AccT, int CTS, int NCH, bool S2S>
+template <typename AccT, int CTS, int NCH, bool S2S, int FV>
 static void launch_pbs_ring_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
                               const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     const size_t smem = (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>) + (size_t)CTS * 2 * 1024 * sizeof(cplx) +
                         (size_t)NCH * kChunkCplx * sizeof(cplx) + (S2S ? 16 * 32 * sizeof(cplx) : 0) + 2 * NCH * sizeof(uint64_t);
     static bool configured = false;
     if (!configured) {
-        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_ring_kernel<AccT, CTS, NCH, S2S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_ring_kernel<AccT, CTS, NCH, S2S, FV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     const int grid = (count + CTS - 1) / CTS;
-    pbs_ring_kernel<AccT, CTS, NCH, S2S><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log,
+    pbs_ring_kernel<AccT, CTS, NCH, S2S, FV><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log,
                                                                         luts, lut_idx, out_big, out_idx, count);
 }
 
 static int pbs_variant() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("FSC_PBS_VARIANT");      // "pair" | "ring" | "s2smem" (default)
-        v = (e && e[0] == 'p') ? 0 : (e && e[0] == 'r') ? 1 : 2;
+        const char* e = getenv("FSC_PBS_VARIANT");      // "pair" (first version, kept for comparison) | "ring" (default)
+        v = (e && e[0] == 'p') ? 0 : 1;
     }
     return v;
 }
 
+// Ring kernel configuration by batch width: wide levels pack 4 (u32 accumulator) or 3 (u64) ciphertexts per CTA
+// to share every key chunk; narrow levels (at most one or two ciphertexts per SM) use 1 or 2 per CTA so that each
+// ciphertext gets a less contended SM and the whole step's key fits in the ring - that is the latency-bound case
+// of the carry-propagation levels.
 void launch_pbs(int acc_bits, const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
-                const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
+                const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, int sm_count, cudaStream_t st) {
     if (count <= 0) return;
+#define FSC_RING(ACC, CTS, NCH) \
+    launch_pbs_ring_t<ACC, CTS, NCH, true, 0>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st)
     if (pbs_variant() == 0) {
         if (acc_bits == 32) launch_pbs_pair_t<uint32_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
         else launch_pbs_pair_t<uint64_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
-    } else if (pbs_variant() == 2) {
-        if (acc_bits == 32) launch_pbs_ring_t<uint32_t, 4, 3, true>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
-        else launch_pbs_ring_t<uint64_t, 3, 3, true>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
+    } else if (acc_bits == 32) {
+        if (count <= sm_count) FSC_RING(uint32_t, 1, 10);
+        else if (count <= 2 * sm_count) FSC_RING(uint32_t, 2, 10);
+        else FSC_RING(uint32_t, 4, 3);
     } else {
-        if (acc_bits == 32) launch_pbs_ring_t<uint32_t, 4, 4, false>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
-        else launch_pbs_ring_t<uint64_t, 3, 4, false>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
+        if (count <= sm_count) FSC_RING(uint64_t, 1, 10);
+        else if (count <= 2 * sm_count) FSC_RING(uint64_t, 2, 10);
+        else FSC_RING(uint64_t, 3, 3);
     }
+#undef FSC_RING
 }
 
 // ---------------------------------------------------------------------------------------
