@@ -53,4 +53,6 @@ void launch_lincomb(const uint64_t* pool, const int32_t* row_ptr, const int32_t*
                     const int32_t* cst, uint64_t delta, uint64_t* out, const int32_t* dst_idx, int count, int words,
                     cudaStream_t st);
 
+void launch_scatter(const uint64_t* buffer, const int32_t* dst_idx, uint64_t* pool, int count, int words, cudaStream_t st);
+
 }  // namespace fsc

@@ -24,6 +24,19 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const uint64_t* __restrict
     }
 }
 
+// pool[dst[b]] = buffer[b]  (placing an all-gathered level into its pool slots)
+__global__ void __launch_bounds__(256) scatter_kernel(const uint64_t* __restrict__ buffer, const int32_t* __restrict__ dst_idx,
+                                                       uint64_t* __restrict__ pool, int words) {
+    const int b = blockIdx.x;
+    const uint64_t* src = buffer + (size_t)b * words;
+    uint64_t* o = pool + (size_t)dst_idx[b] * words;
+    for (int w = threadIdx.x; w < words; w += blockDim.x) o[w] = src[w];
+}
+void launch_scatter(const uint64_t* buffer, const int32_t* dst_idx, uint64_t* pool, int count, int words, cudaStream_t st) {
+    if (count <= 0) return;
+    scatter_kernel<<<count, 256, 0, st>>>(buffer, dst_idx, pool, words);
+}
+
 void launch_lincomb(const uint64_t* pool, const int32_t* row_ptr, const int32_t* slot, const int32_t* coef, const int32_t* cst,
                     uint64_t delta, uint64_t* out, const int32_t* dst_idx, int count, int words, cudaStream_t st) {
     if (count <= 0) return;

@@ -15,6 +15,7 @@
 #pragma once
 #include <stdint.h>
 
+#include <algorithm>
 #include <array>
 #include <map>
 #include <memory>
@@ -49,10 +50,32 @@ struct LinReq {
     int32_t dst = -1;
 };
 
+// Multi-GPU: a level of at least min_width requests is cut into `world` contiguous slices of `per` requests;
+// rank r bootstraps slice r into buffer[r * per ...] and the caller-provided all-gather completes the buffer on
+// every rank (keys are replicated, so nothing else moves).  The callback enqueues the collective on the
+// context's stream (NCCL over NVLink through torch.distributed in fhe_sign_b200/distributed.py).
+typedef int32_t (*ExchangeFn)(void* user, void* buffer, size_t bytes_per_rank);
+struct Exchange {
+    int rank = 0, world = 1;
+    size_t min_width = 0;
+    void* buffer = nullptr;
+    size_t capacity = 0;
+    ExchangeFn all_gather = nullptr;
+    void* user = nullptr;
+    bool active(size_t count) const { return world > 1 && all_gather && count >= min_width; }
+};
+inline void shard_range(size_t count, int rank, int world, size_t* per, size_t* lo, size_t* hi) {
+    *per = (count + world - 1) / world;
+    *lo = std::min(count, (size_t)rank * *per);
+    *hi = std::min(count, *lo + *per);
+}
+
 // Device (or mock) side of the radix layer.
 class RadixBackend {
 public:
     virtual ~RadixBackend() {}
+    Exchange exchange;
+    uint64_t sharded_levels = 0;
     virtual int32_t alloc_slot() = 0;
     virtual void free_slot(int32_t s) = 0;
     virtual int32_t lut_id(const LutTable& t) = 0;

@@ -214,4 +214,23 @@ fsc_status fsc_radix_stats(const fsc_ctx* ctx, uint64_t* pbs_count, uint64_t* le
     return FSC_OK;
 }
 
+fsc_status fsc_radix_stats2(const fsc_ctx* ctx, uint64_t* pbs_count, uint64_t* level_count, uint64_t* sharded_levels) {
+    if (!ctx || !ctx->rb) return FSC_ERR_BAD_ARG;
+    if (pbs_count) *pbs_count = ctx->rb->pbs_count;
+    if (level_count) *level_count = ctx->rb->level_count;
+    if (sharded_levels) *sharded_levels = ctx->rb->sharded_levels;
+    return FSC_OK;
+}
+
+fsc_status fsc_set_level_exchange(fsc_ctx* ctx, int32_t rank, int32_t world, size_t min_width, void* buffer, size_t capacity_bytes,
+                                  fsc_exchange_fn all_gather, void* user) {
+    RX_BEGIN(ctx)
+    need(world >= 1 && rank >= 0 && rank < world, "rank / world out of range");
+    need(world == 1 || (buffer && all_gather && capacity_bytes), "exchange buffer and callback are required when world > 1");
+    fsc::Exchange& x = ctx->rb->exchange;
+    x.rank = rank; x.world = world; x.min_width = min_width; x.buffer = buffer; x.capacity = capacity_bytes;
+    x.all_gather = all_gather; x.user = user;
+    RX_END(ctx)
+}
+
 }  // extern "C"

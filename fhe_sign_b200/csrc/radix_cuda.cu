@@ -169,6 +169,7 @@ public:
     void run_level(const std::vector<LevelReq>& reqs) override {
         if (reqs.empty()) return;
         eng->use();
+        if (exchange.active(reqs.size())) { run_level_sharded(reqs); return; }
         ensure_stage_big(reqs.size());
         eng->ensure_scratch(reqs.size());
         const Csr c = upload(reqs, true);
@@ -177,6 +178,30 @@ public:
         FSC_CUDA_CHECK(cudaGetLastError());
         eng->keyswitch(stage_big, eng->scratch_small, c.count);
         eng->pbs(eng->scratch_small, &luts, c.lut, pool, c.count, c.dst);
+    }
+    // this rank bootstraps its contiguous slice into the exchange buffer, all ranks all-gather, every rank scatters
+    void run_level_sharded(const std::vector<LevelReq>& reqs) {
+        size_t per, lo, hi;
+        shard_range(reqs.size(), exchange.rank, exchange.world, &per, &lo, &hi);
+        const size_t slice_bytes = per * words * 8;
+        if (slice_bytes * exchange.world > exchange.capacity) throw Error(FSC_ERR_COMM, "level exchange buffer too small for this level");
+        const size_t mine = hi - lo;
+        ensure_stage_big(std::max<size_t>(mine, 1));
+        eng->ensure_scratch(std::max<size_t>(mine, 1));
+        const Csr c = upload(reqs, true);
+        uint64_t* xb = static_cast<uint64_t*>(exchange.buffer);
+        if (mine) {
+            launch_lincomb(pool, c.row_ptr + lo, c.slot, c.coef, c.cst + lo, delta, stage_big, nullptr, (int)mine, (int)words, eng->stream);
+            ++eng->launches;
+            FSC_CUDA_CHECK(cudaGetLastError());
+            eng->keyswitch(stage_big, eng->scratch_small, mine);
+            eng->pbs(eng->scratch_small, &luts, c.lut + lo, xb + lo * words, mine, nullptr);
+        }
+        if (exchange.all_gather(exchange.user, exchange.buffer, slice_bytes) != 0) throw Error(FSC_ERR_COMM, "level all-gather failed");
+        launch_scatter(xb, c.dst, pool, (int)reqs.size(), (int)words, eng->stream);
+        ++eng->launches;
+        FSC_CUDA_CHECK(cudaGetLastError());
+        ++sharded_levels;
     }
     void run_linear(const std::vector<LinReq>& reqs) override {
         if (reqs.empty()) return;

@@ -1,0 +1,58 @@
+"""Multi-GPU level sharding: one process per GPU, replicated keys, NCCL all-gather of PBS level outputs.
+
+`enable_level_sharding(ctx, ...)` allocates the exchange buffer as a torch tensor on the context's device and
+installs an all-gather callback (fsc_set_level_exchange) that runs `torch.distributed.all_gather_into_tensor`
+over it — NCCL over NVLink 5 / NVSwitch on a B200 node, gloo in the CPU tests.  Every rank must issue the same
+operator sequence (SPMD); levels narrower than `min_width` run replicated with no communication.
+"""
+import ctypes as C
+
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+def make_all_gather(buffer_tensor, group=None):
+    """Returns (callback object, keepalive) all-gathering equal slices of `buffer_tensor` in place."""
+    import torch
+    import torch.distributed as dist
+
+    flat = buffer_tensor.view(torch.uint8).reshape(-1)
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+
+    def _cb(user, buf, bytes_per_rank):
+        try:
+            total = bytes_per_rank * world
+            out = flat[:total]
+            mine = flat[rank * bytes_per_rank:(rank + 1) * bytes_per_rank]
+            if flat.is_cuda:
+                dist.all_gather_into_tensor(out, mine, group=group)
+            else:
+                # gloo: gather into a list of views, then copy back into place
+                parts = [torch.empty(bytes_per_rank, dtype=torch.uint8) for _ in range(world)]
+                dist.all_gather(parts, mine.clone(), group=group)
+                for r, p in enumerate(parts):
+                    flat[r * bytes_per_rank:(r + 1) * bytes_per_rank].copy_(p)
+            return 0
+        except Exception as e:      # never let an exception cross the C boundary
+            print("level all-gather failed:", repr(e))
+            return 1
+
+    return EXCHANGE_FN(_cb)
+
+
+def enable_level_sharding(ctx, min_width=1184, capacity_blocks=1 << 16, group=None):
+    """Shard every PBS level of >= min_width requests across the ranks of the default process group.
+
+    `ctx` must have been created on torch's current CUDA stream (Context(..., stream=torch.cuda.current_stream().cuda_stream))
+    so that the collective and the kernels are ordered on one stream."""
+    import torch
+    import torch.distributed as dist
+
+    words = ctx.params.glwe_dim * ctx.params.poly_size + 1
+    buf = torch.empty(capacity_blocks * words, dtype=torch.int64, device="cuda")
+    cb = make_all_gather(buf, group)
+    rc = ctx.L.fsc_set_level_exchange(ctx.h, dist.get_rank(group), dist.get_world_size(group), min_width,
+                                      C.c_void_p(buf.data_ptr()), buf.numel() * 8, cb, None)
+    ctx._check(rc)
+    ctx._exchange_keepalive = (buf, cb)      # the library keeps raw pointers to both
+    return buf

@@ -11,7 +11,8 @@ WORDS = 2049
 
 RADIX_EXPORTS = ["fsc_radix_from_lwe", "fsc_radix_to_lwe", "fsc_radix_trivial", "fsc_radix_clone", "fsc_radix_free",
                  "fsc_radix_len", "fsc_radix_binary", "fsc_radix_scalar", "fsc_radix_mul_wide", "fsc_radix_cast",
-                 "fsc_radix_slice", "fsc_radix_concat", "fsc_radix_sum", "fsc_radix_select", "fsc_radix_stats"]
+                 "fsc_radix_slice", "fsc_radix_concat", "fsc_radix_sum", "fsc_radix_select", "fsc_radix_stats",
+                 "fsc_radix_stats2", "fsc_set_level_exchange"]
 
 
 def declare(L):
@@ -25,6 +26,8 @@ def declare(L):
         "fsc_radix_cast": [vp, vp, sz, pp], "fsc_radix_slice": [vp, vp, sz, sz, pp],
         "fsc_radix_concat": [vp, vp, sz, pp], "fsc_radix_sum": [vp, vp, sz, sz, pp],
         "fsc_radix_select": [vp, vp, vp, vp, pp], "fsc_radix_stats": [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
+        "fsc_radix_stats2": [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
+        "fsc_set_level_exchange": [vp, C.c_int32, C.c_int32, sz, vp, sz, vp, vp],
     }
     for name, args in sig.items():
         f = getattr(L, name)
@@ -125,6 +128,11 @@ class RadixApi:
     def max(self, a, b): return self.binary("max", a, b)
     def lt(self, a, b): return self.binary("lt", a, b)
     def eq(self, a, b): return self.binary("eq", a, b)
+
+    def sharded_levels(self):
+        n = C.c_uint64()
+        self.L.fsc_radix_stats2(self.ctx, None, None, C.byref(n))
+        return n.value
 
     def stats(self):
         p, l = C.c_uint64(), C.c_uint64()

@@ -159,6 +159,18 @@ fsc_status fsc_radix_concat(fsc_ctx *ctx, const fsc_radix *const *parts, size_t 
 fsc_status fsc_radix_sum(fsc_ctx *ctx, const fsc_radix *const *operands, size_t n_operands, size_t n_blocks, fsc_radix **out);
 /* cond ? if_true : if_false; cond is a one-block value holding 0 / 1 (FSC_OP_LT / FSC_OP_EQ output). */
 fsc_status fsc_radix_select(fsc_ctx *ctx, const fsc_radix *cond, const fsc_radix *if_true, const fsc_radix *if_false, fsc_radix **out);
+/* ---- multi-GPU: sharding of wide PBS levels over the ranks of one node ------------------------ */
+/* One process per GPU, keys replicated, every rank runs the same operator sequence.  A PBS level of at least
+ * `min_width` requests is cut into `world` contiguous slices; this rank bootstraps slice `rank` into
+ * buffer[rank * bytes_per_rank ...] and then calls `all_gather`, which must enqueue on the context's stream an
+ * all-gather over that buffer (rank r's slice at offset r * bytes_per_rank on every rank), e.g. NCCL over
+ * NVLink via torch.distributed.  `buffer` is caller-owned device memory of `capacity_bytes`.  Narrower levels
+ * run replicated on every rank with no exchange.  (The reference has no counterpart: rayon threads, one host.) */
+typedef int32_t (*fsc_exchange_fn)(void *user, void *buffer, size_t bytes_per_rank);
+fsc_status fsc_set_level_exchange(fsc_ctx *ctx, int32_t rank, int32_t world, size_t min_width, void *buffer,
+                                  size_t capacity_bytes, fsc_exchange_fn all_gather, void *user);
+/* bootstraps, PBS levels and sharded levels issued by the radix layer so far on this context     */
+fsc_status fsc_radix_stats2(const fsc_ctx *ctx, uint64_t *pbs_count, uint64_t *level_count, uint64_t *sharded_levels);
 /* bootstraps and PBS levels issued by the radix layer so far on this context                      */
 fsc_status fsc_radix_stats(const fsc_ctx *ctx, uint64_t *pbs_count, uint64_t *level_count);
 

@@ -40,7 +40,27 @@ public:
         for (auto& t : terms) v += (long)t.second * val[t.first];
         return (int)(((v % 32) + 32) % 32);
     }
+    // same slicing as the CUDA backend, on a host buffer: one "ciphertext" = 2049 words, body last
+    void run_level_sharded(const std::vector<fsc::LevelReq>& reqs) {
+        size_t per, lo, hi;
+        fsc::shard_range(reqs.size(), exchange.rank, exchange.world, &per, &lo, &hi);
+        const size_t slice_bytes = per * 2049 * 8;
+        if (slice_bytes * exchange.world > exchange.capacity) throw fsc::RadixError("level exchange buffer too small");
+        uint64_t* xb = static_cast<uint64_t*>(exchange.buffer);
+        for (size_t i = lo; i < hi; ++i) {
+            const int v = lin(reqs[i].terms, reqs[i].cst);
+            if (v >= 16) ++violations;
+            const fsc::LutTable& t = luts[reqs[i].lut];
+            const int o = v < 16 ? t[v] : (32 - t[v - 16]) % 32;
+            for (size_t w = 0; w < 2048; ++w) xb[i * 2049 + w] = 0;
+            xb[i * 2049 + 2048] = (uint64_t)o * delta;
+        }
+        if (exchange.all_gather(exchange.user, exchange.buffer, slice_bytes) != 0) throw fsc::RadixError("all-gather failed");
+        for (size_t i = 0; i < reqs.size(); ++i) val[reqs[i].dst] = (int)((xb[i * 2049 + 2048] + delta / 2) / delta) % 32;
+        ++sharded_levels;
+    }
     void run_level(const std::vector<fsc::LevelReq>& reqs) override {
+        if (exchange.active(reqs.size())) { run_level_sharded(reqs); return; }
         std::vector<int> out(reqs.size());
         for (size_t i = 0; i < reqs.size(); ++i) {
             const int v = lin(reqs[i].terms, reqs[i].cst);
