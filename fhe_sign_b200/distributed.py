@@ -10,8 +10,9 @@ import ctypes as C
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t)
 
 
-def make_all_gather(buffer_tensor, group=None):
-    """Returns (callback object, keepalive) all-gathering equal slices of `buffer_tensor` in place."""
+def make_all_gather(buffer_tensor, group=None, stream=None):
+    """Returns the C callback all-gathering equal slices of `buffer_tensor` in place (on `stream` if given)."""
+    import contextlib
     import torch
     import torch.distributed as dist
 
@@ -25,7 +26,8 @@ def make_all_gather(buffer_tensor, group=None):
             out = flat[:total]
             mine = flat[rank * bytes_per_rank:(rank + 1) * bytes_per_rank]
             if flat.is_cuda:
-                dist.all_gather_into_tensor(out, mine, group=group)
+                with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
+                    dist.all_gather_into_tensor(out, mine, group=group)
             else:
                 # gloo: gather into a list of views, then copy back into place
                 parts = [torch.empty(bytes_per_rank, dtype=torch.uint8) for _ in range(world)]
@@ -40,17 +42,20 @@ def make_all_gather(buffer_tensor, group=None):
     return EXCHANGE_FN(_cb)
 
 
-def enable_level_sharding(ctx, min_width=1184, capacity_blocks=1 << 16, group=None):
+def enable_level_sharding(ctx, stream, min_width=1184, capacity_blocks=1 << 16, group=None):
     """Shard every PBS level of >= min_width requests across the ranks of the default process group.
 
-    `ctx` must have been created on torch's current CUDA stream (Context(..., stream=torch.cuda.current_stream().cuda_stream))
-    so that the collective and the kernels are ordered on one stream."""
+    `stream` is the torch.cuda.Stream the context was created on (Context(..., stream=stream.cuda_stream)); it must
+    not be the legacy default stream (handle 0 asks the library for a stream of its own).  The collective is
+    enqueued on that stream, so kernels and all-gathers stay ordered without host synchronisation."""
     import torch
     import torch.distributed as dist
 
+    assert stream.cuda_stream != 0, "create the context on a dedicated torch.cuda.Stream()"
     words = ctx.params.glwe_dim * ctx.params.poly_size + 1
-    buf = torch.empty(capacity_blocks * words, dtype=torch.int64, device="cuda")
-    cb = make_all_gather(buf, group)
+    with torch.cuda.stream(stream):
+        buf = torch.empty(capacity_blocks * words, dtype=torch.int64, device="cuda")
+    cb = make_all_gather(buf, group, stream)
     rc = ctx.L.fsc_set_level_exchange(ctx.h, dist.get_rank(group), dist.get_world_size(group), min_width,
                                       C.c_void_p(buf.data_ptr()), buf.numel() * 8, cb, None)
     ctx._check(rc)
