@@ -95,7 +95,8 @@ EXPORTS = ["fsc_ctx_create", "fsc_ctx_destroy", "fsc_last_error", "fsc_get_param
            "fsc_ks_pbs_batch", "fsc_apply_lut_host", "fsc_timer_start", "fsc_timer_stop", "fsc_launch_count",
            "fsc_debug_negacyclic_mul", "fsc_measure_fp64_peak"]
 from .radix import RADIX_EXPORTS  # noqa: E402
-EXPORTS = EXPORTS + RADIX_EXPORTS
+EXPORTS = EXPORTS + RADIX_EXPORTS + ["fsc_client_keygen", "fsc_client_free", "fsc_client_last_error", "fsc_client_server_keys",
+                                     "fsc_client_secret_keys", "fsc_client_encrypt_blocks", "fsc_client_decrypt_blocks"]
 
 
 def _ptr(a):

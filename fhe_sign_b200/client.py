@@ -1,0 +1,114 @@
+"""Client side (host CPU) of the path over the fsc_client_* C ABI: the ClientKey look-alike.
+
+Mirrors what the reference gets from tfhe: `generate_keys(config)` (src/biguint.rs:277) -> (ClientKey, server key
+material), `FheUint32::try_encrypt(value, &client_key)` (src/biguint.rs:26) and `.decrypt(&client_key)`
+(src/biguint.rs:70)."""
+import ctypes as C
+
+import numpy as np
+
+from .capi import FscError, Params, load_library
+
+WORDS = 2049
+
+NOISE = {
+    "2_2_gaussian": dict(noise_kind=0, lwe_noise_std=3.5539902359442825e-06, glwe_noise_std=2.845267479601915e-15),
+    "2_2_tuniform": dict(noise_kind=1, lwe_tuniform_bound=46, glwe_tuniform_bound=17),
+    "toy": dict(noise_kind=0, lwe_noise_std=3.5539902359442825e-06, glwe_noise_std=2.845267479601915e-15),
+}
+
+
+class NoiseParams(C.Structure):
+    _fields_ = [("noise_kind", C.c_uint32), ("lwe_tuniform_bound", C.c_uint32), ("glwe_tuniform_bound", C.c_uint32),
+                ("reserved", C.c_uint32), ("lwe_noise_std", C.c_double), ("glwe_noise_std", C.c_double)]
+
+
+CLIENT_EXPORTS = ["fsc_client_keygen", "fsc_client_free", "fsc_client_last_error", "fsc_client_server_keys",
+                  "fsc_client_secret_keys", "fsc_client_encrypt_blocks", "fsc_client_decrypt_blocks"]
+
+
+def _declare(L):
+    vp, sz = C.c_void_p, C.c_size_t
+    L.fsc_client_keygen.argtypes = [C.POINTER(Params), C.POINTER(NoiseParams), C.c_uint64, C.POINTER(vp)]
+    L.fsc_client_free.argtypes = [vp]
+    L.fsc_client_last_error.argtypes = [vp]; L.fsc_client_last_error.restype = C.c_char_p
+    L.fsc_client_server_keys.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]
+    L.fsc_client_secret_keys.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.fsc_client_encrypt_blocks.argtypes = [vp, vp, sz, vp]
+    L.fsc_client_decrypt_blocks.argtypes = [vp, vp, sz, vp, vp]
+
+
+class ClientKey:
+    """Secret keys + the server key material derived from them (seeded)."""
+
+    def __init__(self, preset="2_2_gaussian", seed=1):
+        self.L = load_library()
+        _declare(self.L)
+        self.params = Params.preset(preset)
+        self.noise = NoiseParams(**NOISE[preset])
+        h = C.c_void_p()
+        rc = self.L.fsc_client_keygen(C.byref(self.params), C.byref(self.noise), seed, C.byref(h))
+        if rc != 0:
+            raise FscError(rc, (self.L.fsc_client_last_error(None) or b"").decode())
+        self.h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.fsc_client_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise FscError(rc, (self.L.fsc_client_last_error(self.h) or b"").decode())
+
+    def server_keys(self):
+        """(bsk_std, ksk) as numpy views, ready for Context.upload_keys."""
+        b, k, nb, nk = C.c_void_p(), C.c_void_p(), C.c_size_t(), C.c_size_t()
+        self._check(self.L.fsc_client_server_keys(self.h, C.byref(b), C.byref(nb), C.byref(k), C.byref(nk)))
+        bsk = np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_uint64)), shape=(nb.value,))
+        ksk = np.ctypeslib.as_array(C.cast(k, C.POINTER(C.c_uint64)), shape=(nk.value,))
+        return bsk, ksk
+
+    def secret_keys(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(self.L.fsc_client_secret_keys(self.h, C.byref(a), C.byref(b)))
+        lwe = np.ctypeslib.as_array(C.cast(a, C.POINTER(C.c_uint64)), shape=(self.params.lwe_dim,))
+        glwe = np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_uint64)), shape=(self.params.glwe_dim * self.params.poly_size,))
+        return lwe, glwe
+
+    def encrypt_block_values(self, values):
+        values = np.ascontiguousarray(values, dtype=np.uint8)
+        out = np.empty((values.size, WORDS), dtype=np.uint64)
+        self._check(self.L.fsc_client_encrypt_blocks(self.h, values.ctypes.data_as(C.c_void_p), values.size, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def decrypt_block_values(self, blocks, with_noise=False):
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint64).reshape(-1, WORDS)
+        vals = np.empty(blocks.shape[0], dtype=np.uint8)
+        noise = np.empty(blocks.shape[0], dtype=np.int64) if with_noise else None
+        self._check(self.L.fsc_client_decrypt_blocks(self.h, blocks.ctypes.data_as(C.c_void_p), blocks.shape[0], vals.ctypes.data_as(C.c_void_p),
+                                                     None if noise is None else noise.ctypes.data_as(C.c_void_p)))
+        return (vals, noise) if with_noise else vals
+
+    # ---- the surface BigUintFHE uses (FheUint32::try_encrypt / decrypt) ---------------------------------
+    def encrypt_blocks(self, value, n_blocks, api):
+        digits = [(int(value) >> (2 * i)) & 3 for i in range(n_blocks)]
+        return api.from_lwe(self.encrypt_block_values(digits))
+
+    def encrypt_u32(self, value, api):
+        return self.encrypt_blocks(int(value) & 0xFFFFFFFF, 16, api)
+
+    def decrypt(self, r, api):
+        d = self.decrypt_block_values(api.to_lwe(r))
+        if (d >= 4).any():
+            raise ValueError("decrypted block carries are not empty: %s" % d)
+        return sum(int(v) << (2 * i) for i, v in enumerate(d))
+
+
+def generate_keys(preset="2_2_gaussian", seed=1):
+    """tfhe::generate_keys look-alike: returns (client_key, (bsk_std, ksk))."""
+    ck = ClientKey(preset, seed)
+    return ck, ck.server_keys()

@@ -174,6 +174,31 @@ fsc_status fsc_radix_stats2(const fsc_ctx *ctx, uint64_t *pbs_count, uint64_t *l
 /* bootstraps and PBS levels issued by the radix layer so far on this context                      */
 fsc_status fsc_radix_stats(const fsc_ctx *ctx, uint64_t *pbs_count, uint64_t *level_count);
 
+/* ---- client side (host CPU): key generation, block encryption, decryption ------------------- */
+/* Replaces tfhe::generate_keys / FheUintN::try_encrypt / decrypt (src/biguint.rs:26,70,277).  Plain host code;
+ * randomness is a ChaCha20 stream keyed by `seed` (deterministic for reproducible tests).                  */
+enum { FSC_NOISE_GAUSSIAN = 0, FSC_NOISE_TUNIFORM = 1 };
+typedef struct {
+    uint32_t noise_kind;            /* FSC_NOISE_GAUSSIAN: standard deviations below (fractions of q)          */
+    uint32_t lwe_tuniform_bound;    /* FSC_NOISE_TUNIFORM: noise in [-2^b, 2^b]                                */
+    uint32_t glwe_tuniform_bound;
+    uint32_t reserved;
+    double lwe_noise_std;
+    double glwe_noise_std;
+} fsc_noise_params;
+typedef struct fsc_client fsc_client;
+fsc_status fsc_client_keygen(const fsc_params *params, const fsc_noise_params *noise, uint64_t seed, fsc_client **out);
+fsc_status fsc_client_free(fsc_client *c);
+const char *fsc_client_last_error(const fsc_client *c);
+/* server key material for fsc_keys_upload; the pointers stay valid until fsc_client_free            */
+fsc_status fsc_client_server_keys(const fsc_client *c, const uint64_t **bsk, size_t *bsk_words,
+                                  const uint64_t **ksk, size_t *ksk_words);
+fsc_status fsc_client_secret_keys(const fsc_client *c, const uint64_t **lwe_sk, const uint64_t **glwe_sk);
+/* values: one plaintext (message + carry, < message_modulus*carry_modulus) per block -> big LWE blocks */
+fsc_status fsc_client_encrypt_blocks(fsc_client *c, const uint8_t *values, size_t n_blocks, uint64_t *out_blocks);
+/* values: decoded plaintext incl. the padding bit (0..31); noise (optional): signed phase error per block */
+fsc_status fsc_client_decrypt_blocks(fsc_client *c, const uint64_t *blocks, size_t n_blocks, uint8_t *values, int64_t *noise);
+
 /* ---- measurement & test hooks ---------------------------------------------------------- */
 /* CUDA-event timer on the context's stream.                                                      */
 fsc_status fsc_timer_start(fsc_ctx *ctx);

@@ -62,3 +62,22 @@ def test_sign_fhe_with_k0_all_vectors_fused(ck):
         assert sig.to_bytes().hex().upper() == v["reference_signature"]
         if v["reference_matches_csv"]:
             assert sig.to_bytes().hex().upper() == v["csv_signature"].upper()
+
+
+def test_product_only_pipeline_no_oracle():
+    """keys, encryption, GPU evaluation and decryption all through the product's own C ABI (fsc_client_* +
+    fsc_radix_*): the oracle is not involved.  Known answers of src/biguint.rs:407-426 and vector 1 signing."""
+    import fhe_sign_b200 as fsb
+    from fhe_sign_b200.client import generate_keys
+    ck, (bsk, ksk) = generate_keys("2_2_tuniform", seed=2024)
+    ctx = fsb.Context(fsb.Params.preset("2_2_tuniform", acc_bits=32))
+    ctx.upload_keys(bsk, ksk)
+    bg.set_server_key(ctx)
+    a, b = 123456789123456789, 987654321987654321
+    assert (BigUintFHE.new(a, ck) + BigUintFHE.new(b, ck)).to_biguint(ck) == a + b
+    assert (BigUintFHE.new(a, ck) * BigUintFHE.new(b, ck)).to_biguint(ck) == a * b
+    v = GOLDEN[1]
+    d, k0, msg = int(v["secret_key"], 16), int(v["k0"], 16), bytes.fromhex(v["message"])
+    sig = schnorr.sign_fhe_with_k0(msg, k0, d, BigUintFHE.new(d, ck), ck, fused=True)
+    assert sig.to_bytes().hex().upper() == v["reference_signature"] == v["csv_signature"].upper()
+    ctx.close()
