@@ -321,6 +321,25 @@ FSC_HD void xpose_load_inv(int lane, const cplx* xbuf, cplx (&v)[32]) {
     for (int pos = 0; pos < 32; ++pos) v[pos] = xbuf[xaddr(brev5(pos), lane)];
 }
 
+// half-size variant: the transpose goes through an 8 KiB buffer of doubles, real parts first, then imaginary
+// parts (same wavefront count, twice the instructions, half the shared memory)
+FSC_HD void xpose_store_fwd_h(int lane, double* xb, const cplx (&v)[32], int comp) {
+#pragma unroll
+    for (int pos = 0; pos < 32; ++pos) xb[xaddr(brev5(pos), lane)] = comp ? v[pos].y : v[pos].x;
+}
+FSC_HD void xpose_load_fwd_h(int lane, const double* xb, cplx (&v)[32], int comp) {
+#pragma unroll
+    for (int j1 = 0; j1 < 32; ++j1) { if (comp) v[j1].y = xb[xaddr(lane, j1)]; else v[j1].x = xb[xaddr(lane, j1)]; }
+}
+FSC_HD void xpose_store_inv_h(int lane, double* xb, const cplx (&v)[32], int comp) {
+#pragma unroll
+    for (int j1 = 0; j1 < 32; ++j1) xb[xaddr(lane, j1)] = comp ? v[j1].y : v[j1].x;
+}
+FSC_HD void xpose_load_inv_h(int lane, const double* xb, cplx (&v)[32], int comp) {
+#pragma unroll
+    for (int pos = 0; pos < 32; ++pos) { if (comp) v[pos].y = xb[xaddr(brev5(pos), lane)]; else v[pos].x = xb[xaddr(brev5(pos), lane)]; }
+}
+
 // ---- accumulator arithmetic -------------------------------------------------------------
 // The accumulator polynomial is stored folded: pair idx (< 1024) holds coefficients idx and
 // idx + 1024, so that one 2-word access feeds one complex FFT input and X^1024 is a swap+negate.

@@ -62,6 +62,35 @@ __device__ __forceinline__ void warp_fft_inv_c(int lane, cplx* xbuf, const C2& c
     if (fft_opts<FV>::i1) idft32_dit_twist(v, S1Dev(), TW_BASE);
     else dft32_inv(v, S1PlainDev());
 }
+// same transforms through the 8 KiB half-size transpose buffer
+template <int FV, class C2>
+__device__ __forceinline__ void warp_fft_fwd_h(int lane, double* xb, const C2& c2, cplx (&v)[32]) {
+    if (fft_opts<FV>::f1) dft32_fwd_tan<kP1Center, kP1MinLevel>(v, S1Dev());
+    else dft32_fwd(v, S1PlainDev());
+    xpose_store_fwd_h(lane, xb, v, 0);
+    __syncwarp();
+    xpose_load_fwd_h(lane, xb, v, 0);      // v[].x: transposed real parts; v[].y: still the untransposed imaginary parts
+    __syncwarp();
+    xpose_store_fwd_h(lane, xb, v, 1);
+    __syncwarp();
+    xpose_load_fwd_h(lane, xb, v, 1);
+    __syncwarp();
+    dft32_fwd_tan<kP2Center, fft_opts<FV>::p2_min_level>(v, c2);
+}
+template <int FV, int TW_BASE, class C2>
+__device__ __forceinline__ void warp_fft_inv_h(int lane, double* xb, const C2& c2, cplx (&v)[32]) {
+    dft32_inv_tan<kP2Center, fft_opts<FV>::p2_min_level>(v, c2);
+    xpose_store_inv_h(lane, xb, v, 0);
+    __syncwarp();
+    xpose_load_inv_h(lane, xb, v, 0);
+    __syncwarp();
+    xpose_store_inv_h(lane, xb, v, 1);
+    __syncwarp();
+    xpose_load_inv_h(lane, xb, v, 1);
+    __syncwarp();
+    if (fft_opts<FV>::i1) idft32_dit_twist(v, S1Dev(), TW_BASE);
+    else dft32_inv(v, S1PlainDev());
+}
 template <int FV, typename AccT>
 __device__ __forceinline__ void tail_fv(int lane, pair_t<AccT>* acc, const cplx (&v)[32]) {
     if (fft_opts<FV>::i1) cmux_tail_scaled<AccT>(lane, acc, v);
@@ -238,15 +267,16 @@ __device__ __forceinline__ void pair_barrier(int id) {      // the two warps of 
     asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
 
-template <typename AccT, int CTS, int NCH, bool S2S, int FV>
+template <typename AccT, int CTS, int NCH, bool S2S, int FV, bool XH>
 __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                                      int n, int base_log, const uint64_t* __restrict__ luts,
                                                                      const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
                                                                      const int32_t* __restrict__ out_idx, int count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pair_t<AccT>* acc_all = reinterpret_cast<pair_t<AccT>*>(smem_raw);
+    constexpr int kXb = XH ? 512 : 1024;                 // transpose / exchange buffer per warp, in complex units
     cplx* xbuf_all = reinterpret_cast<cplx*>(smem_raw + (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>));
-    cplx* ring = xbuf_all + (size_t)CTS * 2 * 1024;
+    cplx* ring = xbuf_all + (size_t)CTS * 2 * kXb;
     cplx* s2tab = ring + (size_t)NCH * kChunkCplx;
     uint64_t* full = reinterpret_cast<uint64_t*>(s2tab + (S2S ? 16 * 32 : 0));
     uint64_t* empty = full + NCH;
@@ -273,8 +303,8 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
     const bool live = c_raw < count;
     const int c = live ? c_raw : count - 1;            // padding warps shadow the last ciphertext, never store
     pair_t<AccT>* acc = acc_all + (size_t)(ctl * 2 + p) * 1024;
-    cplx* xbuf = xbuf_all + (size_t)(ctl * 2 + p) * 1024;
-    const cplx* xother = xbuf_all + (size_t)(ctl * 2 + (1 - p)) * 1024;
+    cplx* xbuf = xbuf_all + (size_t)(ctl * 2 + p) * kXb;
+    const cplx* xother = xbuf_all + (size_t)(ctl * 2 + (1 - p)) * kXb;
     const uint64_t* ct = in_small + (size_t)c * (n + 1);
     const uint64_t* lut = luts + (size_t)(lut_idx ? lut_idx[c] : 0) * kN;
 
@@ -313,42 +343,49 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
 
         cplx X[32];
         cmux_head<AccT>(lane, acc, a, base_log, X);
-        if (S2S) warp_fft_fwd_c<FV>(lane, xbuf, c2s, X);
+        if (XH) warp_fft_fwd_h<FV>(lane, reinterpret_cast<double*>(xbuf), c2s, X);
+        else if (S2S) warp_fft_fwd_c<FV>(lane, xbuf, c2s, X);
         else warp_fft_fwd_c<FV>(lane, xbuf, RegConsts(reinterpret_cast<cplx(&)[16]>(s2)), X);
-#pragma unroll
-        for (int r = 0; r < 32; ++r) xbuf[r * 32 + lane] = X[r];
-        pair_barrier(1 + ctl);
 
+        // Fourier-domain product; with the half-size buffer the spectra are swapped 16 slots at a time
 #pragma unroll
-        for (int k = 0; k < kChunksPerStep; ++k, ++t) {
-            const int stage = t % NCH;
-            mbar_wait(full + stage, (uint32_t)(t / NCH) & 1);
-            const cplx* g = ring + (size_t)stage * kChunkCplx + lane;
+        for (int half = 0; half < (XH ? 2 : 1); ++half) {
+            constexpr int kSlots = XH ? 16 : 32;
 #pragma unroll
-            for (int rr = 0; rr < kChunkSlots; ++rr) {
-                const int r = k * kChunkSlots + rr;
-                const cplx o = xother[r * 32 + lane];
-                const cplx gw = g[(rr * 4 + g_own) * 32], go = g[(rr * 4 + g_oth) * 32];
-                const cplx x = X[r];
-                X[r].x = x.x * gw.x - x.y * gw.y + o.x * go.x - o.y * go.y;
-                X[r].y = x.x * gw.y + x.y * gw.x + o.x * go.y + o.y * go.x;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + stage);
-            if (producer && t >= 1) {
-                // refill the stage released one chunk ago with the chunk NCH-1 ahead of the current one
-                const int u = t - 1 + NCH;
-                if (u < total_chunks) {
-                    const int ps = (t - 1) % NCH;
-                    mbar_wait(empty + ps, (uint32_t)((t - 1) / NCH) & 1);
-                    mbar_arrive_expect_tx(full + ps, kChunkCplx * sizeof(cplx));
-                    bulk_load(ring + (size_t)ps * kChunkCplx, bsk_f + (size_t)u * kChunkCplx, kChunkCplx * sizeof(cplx), full + ps);
+            for (int r = 0; r < kSlots; ++r) xbuf[r * 32 + lane] = X[half * kSlots + r];
+            pair_barrier(1 + ctl);
+#pragma unroll
+            for (int k = 0; k < kSlots / kChunkSlots; ++k, ++t) {
+                const int stage = t % NCH;
+                mbar_wait(full + stage, (uint32_t)(t / NCH) & 1);
+                const cplx* g = ring + (size_t)stage * kChunkCplx + lane;
+#pragma unroll
+                for (int rr = 0; rr < kChunkSlots; ++rr) {
+                    const int rl = k * kChunkSlots + rr, r = half * kSlots + rl;
+                    const cplx o = xother[rl * 32 + lane];
+                    const cplx gw = g[(rr * 4 + g_own) * 32], go = g[(rr * 4 + g_oth) * 32];
+                    const cplx x = X[r];
+                    X[r].x = x.x * gw.x - x.y * gw.y + o.x * go.x - o.y * go.y;
+                    X[r].y = x.x * gw.y + x.y * gw.x + o.x * go.y + o.y * go.x;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + stage);
+                if (producer && t >= 1) {
+                    // refill the stage released one chunk ago with the chunk NCH-1 ahead of the current one
+                    const int u = t - 1 + NCH;
+                    if (u < total_chunks) {
+                        const int ps = (t - 1) % NCH;
+                        mbar_wait(empty + ps, (uint32_t)((t - 1) / NCH) & 1);
+                        mbar_arrive_expect_tx(full + ps, kChunkCplx * sizeof(cplx));
+                        bulk_load(ring + (size_t)ps * kChunkCplx, bsk_f + (size_t)u * kChunkCplx, kChunkCplx * sizeof(cplx), full + ps);
+                    }
                 }
             }
+            pair_barrier(1 + ctl);
         }
-        pair_barrier(1 + ctl);
 
-        if (S2S) warp_fft_inv_c<FV, uni_tw<AccT>::base>(lane, xbuf, c2s, X);
+        if (XH) warp_fft_inv_h<FV, uni_tw<AccT>::base>(lane, reinterpret_cast<double*>(xbuf), c2s, X);
+        else if (S2S) warp_fft_inv_c<FV, uni_tw<AccT>::base>(lane, xbuf, c2s, X);
         else warp_fft_inv_c<FV, uni_tw<AccT>::base>(lane, xbuf, RegConsts(reinterpret_cast<cplx(&)[16]>(s2)), X);
         tail_fv<FV, AccT>(lane, acc, X);
         __syncwarp();
@@ -415,18 +452,18 @@ static void launch_pbs_pair_t(const void* bsk_f, const uint64_t* in_small, int n
                                                     lut_idx, out_big, out_idx, count);
 }
 
-template <typename AccT, int CTS, int NCH, bool S2S, int FV>
+template <typename AccT, int CTS, int NCH, bool S2S, int FV, bool XH = false>
 static void launch_pbs_ring_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
                               const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
-    const size_t smem = (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>) + (size_t)CTS * 2 * 1024 * sizeof(cplx) +
+    const size_t smem = (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>) + (size_t)CTS * 2 * (XH ? 512 : 1024) * sizeof(cplx) +
                         (size_t)NCH * kChunkCplx * sizeof(cplx) + (S2S ? 16 * 32 * sizeof(cplx) : 0) + 2 * NCH * sizeof(uint64_t);
     static bool configured = false;
     if (!configured) {
-        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_ring_kernel<AccT, CTS, NCH, S2S, FV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_ring_kernel<AccT, CTS, NCH, S2S, FV, XH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     const int grid = (count + CTS - 1) / CTS;
-    pbs_ring_kernel<AccT, CTS, NCH, S2S, FV><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log,
+    pbs_ring_kernel<AccT, CTS, NCH, S2S, FV, XH><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log,
                                                                         luts, lut_idx, out_big, out_idx, count);
 }
 
@@ -454,6 +491,7 @@ void launch_pbs(int acc_bits, const void* bsk_f, const uint64_t* in_small, int n
     } else if (acc_bits == 32) {
         if (count <= sm_count) FSC_RING(uint32_t, 1, 10);
         else if (count <= 2 * sm_count) FSC_RING(uint32_t, 2, 10);
+        else if (getenv("FSC_PBS_XH")) launch_pbs_ring_t<uint32_t, 4, 11, true, 0, true>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
         else FSC_RING(uint32_t, 4, 3);
     } else {
         if (count <= sm_count) FSC_RING(uint64_t, 1, 10);

@@ -80,18 +80,23 @@ static inline int64_t noise_glwe(const orc_params *p, orc_rng *r) {
 
 /* ===================================================================================== */
 /* negacyclic FFT: N reals -> M=N/2 complex, X_k = sum_j (a_j + i a_{j+M}) zeta^{j(4k+1)},  */
-/* zeta = exp(2 pi i / 2N).  Forward = twist + DIF (natural in, bit-reversed out);        */
-/* inverse = DIT (bit-reversed in, natural out) + untwist.  Point-wise products happen in */
-/* the bit-reversed order, so no permutation pass is needed.                              */
+/* zeta = exp(2 pi i / 2N).  Forward = twist + radix-4 DIF (natural in, scrambled out);   */
+/* inverse = the exact stage-wise reverse + untwist.  Point-wise products happen in       */
+/* the scrambled order, so no permutation pass is needed.                                 */
 /* ===================================================================================== */
 typedef struct {
     uint32_t N, M;
-    double *twr, *twi;    /* twist zeta^j, j<M                                   */
-    double *wr, *wi;      /* stage twiddles: w[h+j] = exp(2 pi i j / (2h)), j<h    */
+    double *twr, *twi;    /* twist zeta^j, j<M                                                  */
+    double *w1r, *w1i, *w2r, *w2i, *w3r, *w3i;   /* radix-4 stage twiddles, stage with quarter q at offset q-1... see plan_get */
+    int has_radix2;       /* one leading radix-2 stage when log2 M is odd                        */
+    double *r2r, *r2i;    /* twiddles of that radix-2 stage: exp(2 pi i j / M), j < M/2           */
 } fft_plan;
 
 static fft_plan *g_plans[32];
 
+/* Radix-4 decimation in frequency (natural in, digit-reversed out) for the forward transform and its exact
+ * stage-by-stage inverse (decimation in time) for the backward one; an extra radix-2 stage in front when
+ * log2 M is odd.  Point-wise products happen in the scrambled order, so no permutation pass is needed. */
 static fft_plan *plan_get(uint32_t N) {
     int lg = 0; while ((1u << lg) < N) lg++;
     fft_plan *pl = g_plans[lg];
@@ -99,20 +104,36 @@ static fft_plan *plan_get(uint32_t N) {
 #pragma omp critical(orc_plan)
     {
         if (!g_plans[lg]) {
-            fft_plan *q = (fft_plan *)malloc(sizeof *q);
+            fft_plan *q = (fft_plan *)calloc(1, sizeof *q);
+            const long double PI = 3.14159265358979323846264338327950288L;
             uint32_t M = N / 2;
             q->N = N; q->M = M;
             q->twr = (double *)malloc(sizeof(double) * M); q->twi = (double *)malloc(sizeof(double) * M);
-            q->wr = (double *)malloc(sizeof(double) * M);  q->wi = (double *)malloc(sizeof(double) * M);
             for (uint32_t j = 0; j < M; j++) {
-                long double a = 3.14159265358979323846264338327950288L * (long double)j / (long double)N;
+                long double a = PI * (long double)j / (long double)N;
                 q->twr[j] = (double)cosl(a); q->twi[j] = (double)sinl(a);
             }
-            q->wr[0] = 1; q->wi[0] = 0;
-            for (uint32_t h = 1; h < M; h <<= 1)
-                for (uint32_t j = 0; j < h; j++) {
-                    long double a = 3.14159265358979323846264338327950288L * (long double)j / (long double)h;
-                    q->wr[h + j] = (double)cosl(a); q->wi[h + j] = (double)sinl(a);
+            int lm = lg - 1;
+            q->has_radix2 = lm & 1;
+            uint32_t R = q->has_radix2 ? M / 2 : M;      /* size handled by the radix-4 stages */
+            if (q->has_radix2) {
+                q->r2r = (double *)malloc(sizeof(double) * (M / 2)); q->r2i = (double *)malloc(sizeof(double) * (M / 2));
+                for (uint32_t j = 0; j < M / 2; j++) {
+                    long double a = 2 * PI * (long double)j / (long double)M;
+                    q->r2r[j] = (double)cosl(a); q->r2i[j] = (double)sinl(a);
+                }
+            }
+            /* tables: for every quarter size qq = R/4, R/16, ..., 1 the arrays w^j, w^2j, w^3j (j < qq), w = exp(2 pi i / 4qq);
+             * stage with quarter qq is stored at offset (qq - 1) / 3 * ... -> simply at offset qq - 1 in arrays of size R */
+            q->w1r = (double *)calloc(R, sizeof(double)); q->w1i = (double *)calloc(R, sizeof(double));
+            q->w2r = (double *)calloc(R, sizeof(double)); q->w2i = (double *)calloc(R, sizeof(double));
+            q->w3r = (double *)calloc(R, sizeof(double)); q->w3i = (double *)calloc(R, sizeof(double));
+            for (uint32_t qq = 1; qq < R; qq <<= 2)
+                for (uint32_t j = 0; j < qq; j++) {
+                    long double a = 2 * PI * (long double)j / (long double)(4 * qq);
+                    q->w1r[qq - 1 + j] = (double)cosl(a);     q->w1i[qq - 1 + j] = (double)sinl(a);
+                    q->w2r[qq - 1 + j] = (double)cosl(2 * a); q->w2i[qq - 1 + j] = (double)sinl(2 * a);
+                    q->w3r[qq - 1 + j] = (double)cosl(3 * a); q->w3i[qq - 1 + j] = (double)sinl(3 * a);
                 }
             g_plans[lg] = q;
         }
@@ -120,7 +141,52 @@ static fft_plan *plan_get(uint32_t N) {
     return g_plans[lg];
 }
 
-/* in: real coefficients as doubles c[0..N); out: re/im [M] (bit-reversed order) */
+/* radix-4 DIF stages over `len` points starting at re/im */
+static void r4_fwd(const fft_plan *pl, double *re, double *im, uint32_t len) {
+    for (uint32_t q = len >> 2; q >= 1; q >>= 2) {
+        const double *w1r = pl->w1r + q - 1, *w1i = pl->w1i + q - 1, *w2r = pl->w2r + q - 1, *w2i = pl->w2i + q - 1,
+                     *w3r = pl->w3r + q - 1, *w3i = pl->w3i + q - 1;
+        for (uint32_t s = 0; s < len; s += 4 * q) {
+            double *ar = re + s, *ai = im + s, *br = ar + q, *bi = ai + q, *cr = br + q, *ci = bi + q, *dr = cr + q, *di = ci + q;
+            for (uint32_t j = 0; j < q; j++) {
+                const double t0r = ar[j] + cr[j], t0i = ai[j] + ci[j], t1r = ar[j] - cr[j], t1i = ai[j] - ci[j];
+                const double t2r = br[j] + dr[j], t2i = bi[j] + di[j];
+                const double t3r = -(bi[j] - di[j]), t3i = br[j] - dr[j];          /* i * (b - d) */
+                const double y1r = t1r + t3r, y1i = t1i + t3i, y2r = t0r - t2r, y2i = t0i - t2i, y3r = t1r - t3r, y3i = t1i - t3i;
+                ar[j] = t0r + t2r; ai[j] = t0i + t2i;
+                br[j] = y1r * w1r[j] - y1i * w1i[j]; bi[j] = y1r * w1i[j] + y1i * w1r[j];
+                cr[j] = y2r * w2r[j] - y2i * w2i[j]; ci[j] = y2r * w2i[j] + y2i * w2r[j];
+                dr[j] = y3r * w3r[j] - y3i * w3i[j]; di[j] = y3r * w3i[j] + y3i * w3r[j];
+            }
+            if (q == 1) continue;
+        }
+    }
+}
+/* exact inverse of r4_fwd up to a factor len */
+static void r4_inv(const fft_plan *pl, double *re, double *im, uint32_t len) {
+    for (uint32_t q = 1; q < len; q <<= 2) {
+        const double *w1r = pl->w1r + q - 1, *w1i = pl->w1i + q - 1, *w2r = pl->w2r + q - 1, *w2i = pl->w2i + q - 1,
+                     *w3r = pl->w3r + q - 1, *w3i = pl->w3i + q - 1;
+        for (uint32_t s = 0; s < len; s += 4 * q) {
+            double *ar = re + s, *ai = im + s, *br = ar + q, *bi = ai + q, *cr = br + q, *ci = bi + q, *dr = cr + q, *di = ci + q;
+            for (uint32_t j = 0; j < q; j++) {
+                const double y0r = ar[j], y0i = ai[j];
+                const double y1r = br[j] * w1r[j] + bi[j] * w1i[j], y1i = bi[j] * w1r[j] - br[j] * w1i[j];   /* times conj(w^j) */
+                const double y2r = cr[j] * w2r[j] + ci[j] * w2i[j], y2i = ci[j] * w2r[j] - cr[j] * w2i[j];
+                const double y3r = dr[j] * w3r[j] + di[j] * w3i[j], y3i = di[j] * w3r[j] - dr[j] * w3i[j];
+                const double s0r = y0r + y2r, s0i = y0i + y2i, s1r = y0r - y2r, s1i = y0i - y2i;
+                const double s2r = y1r + y3r, s2i = y1i + y3i;
+                const double s3r = y1i - y3i, s3i = -(y1r - y3r);                   /* -i * (y1 - y3) */
+                ar[j] = s0r + s2r; ai[j] = s0i + s2i;
+                br[j] = s1r + s3r; bi[j] = s1i + s3i;
+                cr[j] = s0r - s2r; ci[j] = s0i - s2i;
+                dr[j] = s1r - s3r; di[j] = s1i - s3i;
+            }
+        }
+    }
+}
+
+/* in: real coefficients as doubles c[0..N); out: re/im [M] (scrambled order) */
 static void fft_fwd(const fft_plan *pl, const double *c, double *re, double *im) {
     const uint32_t M = pl->M;
     for (uint32_t j = 0; j < M; j++) {
@@ -128,36 +194,36 @@ static void fft_fwd(const fft_plan *pl, const double *c, double *re, double *im)
         re[j] = a * pl->twr[j] - b * pl->twi[j];
         im[j] = a * pl->twi[j] + b * pl->twr[j];
     }
-    for (uint32_t h = M >> 1; h >= 1; h >>= 1) {
-        const double *wr = pl->wr + h, *wi = pl->wi + h;
-        for (uint32_t s = 0; s < M; s += 2 * h) {
-            double *r0 = re + s, *i0 = im + s, *r1 = re + s + h, *i1 = im + s + h;
-            for (uint32_t j = 0; j < h; j++) {
-                double ur = r0[j], ui = i0[j], vr = r1[j], vi = i1[j];
-                double dr = ur - vr, di = ui - vi;
-                r0[j] = ur + vr; i0[j] = ui + vi;
-                r1[j] = dr * wr[j] - di * wi[j];
-                i1[j] = dr * wi[j] + di * wr[j];
-            }
+    if (pl->has_radix2) {
+        const uint32_t h = M / 2;
+        for (uint32_t j = 0; j < h; j++) {
+            double ur = re[j], ui = im[j], vr = re[j + h], vi = im[j + h];
+            double dr = ur - vr, di = ui - vi;
+            re[j] = ur + vr; im[j] = ui + vi;
+            re[j + h] = dr * pl->r2r[j] - di * pl->r2i[j];
+            im[j + h] = dr * pl->r2i[j] + di * pl->r2r[j];
         }
+        r4_fwd(pl, re, im, h); r4_fwd(pl, re + h, im + h, h);
+    } else {
+        r4_fwd(pl, re, im, M);
     }
 }
 
-/* in: re/im [M] bit-reversed (destroyed); out: N real coefficients (scaled by 1/M) */
+/* in: re/im [M] scrambled (destroyed); out: N real coefficients (scaled by 1/M) */
 static void fft_inv(const fft_plan *pl, double *re, double *im, double *c) {
     const uint32_t M = pl->M;
-    for (uint32_t h = 1; h < M; h <<= 1) {
-        const double *wr = pl->wr + h, *wi = pl->wi + h;
-        for (uint32_t s = 0; s < M; s += 2 * h) {
-            double *r0 = re + s, *i0 = im + s, *r1 = re + s + h, *i1 = im + s + h;
-            for (uint32_t j = 0; j < h; j++) {
-                double vr = r1[j] * wr[j] + i1[j] * wi[j];   /* times conj(w) */
-                double vi = i1[j] * wr[j] - r1[j] * wi[j];
-                double ur = r0[j], ui = i0[j];
-                r0[j] = ur + vr; i0[j] = ui + vi;
-                r1[j] = ur - vr; i1[j] = ui - vi;
-            }
+    if (pl->has_radix2) {
+        const uint32_t h = M / 2;
+        r4_inv(pl, re, im, h); r4_inv(pl, re + h, im + h, h);
+        for (uint32_t j = 0; j < h; j++) {
+            double vr = re[j + h] * pl->r2r[j] + im[j + h] * pl->r2i[j];
+            double vi = im[j + h] * pl->r2r[j] - re[j + h] * pl->r2i[j];
+            double ur = re[j], ui = im[j];
+            re[j] = ur + vr; im[j] = ui + vi;
+            re[j + h] = ur - vr; im[j + h] = ui - vi;
         }
+    } else {
+        r4_inv(pl, re, im, M);
     }
     const double sc = 1.0 / (double)M;
     for (uint32_t j = 0; j < M; j++) {
@@ -427,7 +493,15 @@ static void external_product_add(const orc_keys *K, uint32_t i, pbs_scratch *s) 
     for (uint32_t pp = 0; pp < k1; pp++)
         for (uint32_t l = 0; l < L; l++) {
             const uint64_t *d = s->rot + (size_t)pp * N;
-            for (uint32_t j = 0; j < N; j++) { orc_decompose(d[j], p->pbs_base_log, L, dg); s->c[j] = (double)dg[l]; }
+            if (L == 1) {            /* single level: closest multiple of q/B, balanced digit (same rule as orc_decompose) */
+                const uint32_t B = p->pbs_base_log;
+                const uint64_t mask = ((uint64_t)1 << B) - 1, half = (uint64_t)1 << (B - 1);
+                for (uint32_t j = 0; j < N; j++) {
+                    const uint64_t st = (((d[j] >> (64 - B - 1)) + 1) >> 1) & mask;
+                    s->c[j] = (double)(st > half ? (int64_t)st - ((int64_t)1 << B) : (int64_t)st);
+                }
+            } else
+                for (uint32_t j = 0; j < N; j++) { orc_decompose(d[j], p->pbs_base_log, L, dg); s->c[j] = (double)dg[l]; }
             fft_fwd(pl, s->c, s->fre, s->fim);
             for (uint32_t q = 0; q < k1; q++) {
                 const size_t off = ((((size_t)i * k1 + pp) * L + l) * k1 + q) * M;
