@@ -243,8 +243,11 @@ def main():
             "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "lwe_dim": n, "acc_bits": ACC_BITS,
                        "l2": "per-step working set 2x67 MB ciphertexts + 123 MB keys > 126 MB L2 (inputs larger than L2)"},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
-                         "kernel": "pbs_pair_kernel", "ms_per_launch": ms_pbs, "flops_per_pbs": F,
+                         "frac": achieved_tf / fp64_peak if fp64_peak else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one 4096-block launch, ncu --set full capture
+                         # profiles/r01_ncu_key_metrics.json (pbs_ring_kernel, n=834, acc 32): 191.8 MB + 60.3 MB
+                         "traffic": 252.07e6 if (BATCH == 4096 and n == 834 and ACC_BITS == 32) else None,
+                         "kernel": "pbs_ring_kernel", "ms_per_launch": ms_pbs, "flops_per_pbs": F,
                          "peak_source": "measured in this run (fsc_measure_fp64_peak; MEASURED_PEAKS.json has no FP64 figure)",
                          "keyswitch_ms_per_launch": ms_ks,
                          "hbm": {"achieved": hbm_bytes / (ms_pbs * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
