@@ -271,7 +271,7 @@ template <typename AccT, int CTS, int NCH, bool S2S, int FV, bool XH>
 __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                                      int n, int base_log, const uint64_t* __restrict__ luts,
                                                                      const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
-                                                                     const int32_t* __restrict__ out_idx, int count) {
+                                                                     const int32_t* __restrict__ out_idx, int count, int stagger) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pair_t<AccT>* acc_all = reinterpret_cast<pair_t<AccT>*>(smem_raw);
     constexpr int kXb = XH ? 512 : 1024;                 // transpose / exchange buffer per warp, in complex units
@@ -290,8 +290,11 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
 
     const int total_chunks = n * kChunksPerStep;
     const bool producer = threadIdx.x == 0;
+    // the producer runs kAhead chunks ahead of its own consumption; the rest of the ring (NCH - kAhead - 1 chunks)
+    // is slack for ciphertexts of the CTA that trail behind
+    constexpr int kAhead = NCH - 2 < 3 ? NCH - 2 : 3;
     if (producer) {
-        for (int u = 0; u < NCH && u < total_chunks; ++u) {
+        for (int u = 0; u <= kAhead && u < total_chunks; ++u) {
             mbar_arrive_expect_tx(full + u, kChunkCplx * sizeof(cplx));
             bulk_load(ring + (size_t)u * kChunkCplx, bsk_f + (size_t)u * kChunkCplx, kChunkCplx * sizeof(cplx), full + u);
         }
@@ -329,6 +332,16 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
             pair_t<AccT> z; z.x = 0; z.y = 0;
             acc[idx] = p ? lut_pair<AccT>(lut, idx, b) : z;
         }
+    }
+    __syncwarp();
+
+    // De-phase the ciphertexts of the CTA: identical code on identical data keeps all warps in the same phase
+    // (all in shared-memory traffic or all in FP64 work at once); a start offset of ctl * stagger cycles lets the
+    // FP64 phases of one ciphertext overlap the transpose / exchange phases of the others.  Needs a ring deep
+    // enough to hold the spread (the XH configuration).
+    if (stagger > 0 && ctl > 0) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < (long long)ctl * stagger) { }
     }
     __syncwarp();
 
@@ -370,12 +383,13 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty + stage);
-                if (producer && t >= 1) {
-                    // refill the stage released one chunk ago with the chunk NCH-1 ahead of the current one
-                    const int u = t - 1 + NCH;
+                if (producer) {
+                    // fetch the chunk kAhead + 1 ahead into its ring stage, once every warp has released the chunk
+                    // that occupied that stage one ring revolution ago
+                    const int u = t + kAhead + 1;
                     if (u < total_chunks) {
-                        const int ps = (t - 1) % NCH;
-                        mbar_wait(empty + ps, (uint32_t)((t - 1) / NCH) & 1);
+                        const int ps = u % NCH;
+                        if (u >= NCH) mbar_wait(empty + ps, (uint32_t)((u - NCH) / NCH) & 1);
                         mbar_arrive_expect_tx(full + ps, kChunkCplx * sizeof(cplx));
                         bulk_load(ring + (size_t)ps * kChunkCplx, bsk_f + (size_t)u * kChunkCplx, kChunkCplx * sizeof(cplx), full + ps);
                     }
@@ -462,9 +476,11 @@ static void launch_pbs_ring_t(const void* bsk_f, const uint64_t* in_small, int n
         FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_ring_kernel<AccT, CTS, NCH, S2S, FV, XH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
+    static int stagger = -1;
+    if (stagger < 0) { const char* e = getenv("FSC_PBS_STAGGER"); stagger = e ? atoi(e) : 0; }
     const int grid = (count + CTS - 1) / CTS;
     pbs_ring_kernel<AccT, CTS, NCH, S2S, FV, XH><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log,
-                                                                        luts, lut_idx, out_big, out_idx, count);
+                                                                        luts, lut_idx, out_big, out_idx, count, stagger);
 }
 
 static int pbs_variant() {
@@ -491,12 +507,13 @@ void launch_pbs(int acc_bits, const void* bsk_f, const uint64_t* in_small, int n
     } else if (acc_bits == 32) {
         if (count <= sm_count) FSC_RING(uint32_t, 1, 10);
         else if (count <= 2 * sm_count) FSC_RING(uint32_t, 2, 10);
-        else if (getenv("FSC_PBS_XH")) launch_pbs_ring_t<uint32_t, 4, 11, true, 0, true>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
-        else FSC_RING(uint32_t, 4, 3);
+        else if (getenv("FSC_PBS_FULLBUF")) FSC_RING(uint32_t, 4, 3);      // 16 KiB transpose buffers, 3-chunk ring
+        else launch_pbs_ring_t<uint32_t, 4, 11, true, 0, true>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
     } else {
         if (count <= sm_count) FSC_RING(uint64_t, 1, 10);
         else if (count <= 2 * sm_count) FSC_RING(uint64_t, 2, 10);
-        else FSC_RING(uint64_t, 3, 3);
+        else if (getenv("FSC_PBS_FULLBUF")) FSC_RING(uint64_t, 3, 3);
+        else launch_pbs_ring_t<uint64_t, 3, 9, true, 0, true>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
     }
 #undef FSC_RING
 }
