@@ -288,12 +288,22 @@ Radix Evaluator::sum_columns(std::vector<std::vector<Block>>& cols) {
         return false;
     };
     while (needs_round()) {
+        // Columns with more than two terms are reduced.  A two-term column that is about to receive a carry from a
+        // reduced neighbour is reduced in the same round: otherwise it would hold three terms in the next round,
+        // pass a carry on, and so forth - one extra PBS level per column of the ripple.
+        std::vector<char> mark(n, 0);
+        for (int c = 0; c < n; ++c) {
+            int deg = 0;
+            for (const auto& b : cols[c]) deg += b.deg;
+            const bool sends_carry = c > 0 && mark[c - 1] == 2;
+            if (cols[c].size() > 2 || (cols[c].size() == 2 && sends_carry)) mark[c] = deg >= 4 ? 2 : 1;   // 2: may emit a carry
+        }
         std::vector<std::vector<Block>> nxt(n);
         std::vector<Req> reqs;
         std::vector<int> dest;
         for (int c = 0; c < n; ++c) {
             auto& col = cols[c];
-            if (col.size() <= 2) { for (auto& b : col) nxt[c].push_back(b); continue; }
+            if (!mark[c]) { for (auto& b : col) nxt[c].push_back(b); continue; }
             // trivial constants first so that they ride along in a chunk for free
             std::stable_sort(col.begin(), col.end(), [](const Block& x, const Block& y) { return x.trivial() > y.trivial(); });
             size_t i = 0;
