@@ -95,7 +95,9 @@ void Engine::upload_keys(const uint64_t* bsk_std, size_t bsk_words, const uint64
     if (e != cudaSuccess) { cudaFree(tmp); FSC_CUDA_CHECK(e); }
     FSC_CUDA_CHECK(cudaMemcpyAsync(tmp, bsk_std, want_bsk * 8, cudaMemcpyHostToDevice, stream));
     FSC_CUDA_CHECK(cudaMemcpyAsync(ksk, ksk_h, want_ksk * 8, cudaMemcpyHostToDevice, stream));
-    launch_bsk_convert(tmp, bsk_f, (int)n, stream); ++launches;
+    if (pbs_variant() == 2) launch_bsk_convert_stream(tmp, bsk_f, (int)n, stream);      // the stream kernel's key order
+    else launch_bsk_convert(tmp, bsk_f, (int)n, stream);
+    ++launches;
     FSC_CUDA_CHECK(cudaGetLastError());
     {
         const size_t K = (size_t)N * p.ks_level;
@@ -173,8 +175,12 @@ void Engine::pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut
                  const int32_t* out_idx_dev) {
     use();
     if (!bsk_f) throw Error(FSC_ERR_NO_KEYS, "server keys not uploaded");
-    launch_pbs((int)p.acc_bits, bsk_f, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, out_big,
-               out_idx_dev, (int)count, sm_count, stream);
+    if (pbs_variant() == 2)
+        launch_pbs_stream((int)p.acc_bits, bsk_f, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, out_big,
+                          out_idx_dev, (int)count, sm_count, stream);
+    else
+        launch_pbs((int)p.acc_bits, bsk_f, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, out_big,
+                   out_idx_dev, (int)count, sm_count, stream);
     ++launches;
     FSC_CUDA_CHECK(cudaGetLastError());
 }
@@ -501,7 +507,10 @@ fsc_status fsc_debug_negacyclic_mul(fsc_ctx* ctx, const uint64_t* a, const int64
     cudaError_t err = cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, e->stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(d + bytes / 8, b, bytes, cudaMemcpyHostToDevice, e->stream);
     if (err == cudaSuccess) {
-        fsc::launch_negacyclic_mul(d, reinterpret_cast<const int64_t*>(d + bytes / 8), d + 2 * (bytes / 8), (int)count, e->stream);
+        if (fsc::pbs_variant() == 2)
+            fsc::launch_negacyclic_mul_stream(d, reinterpret_cast<const int64_t*>(d + bytes / 8), d + 2 * (bytes / 8), (int)count, e->stream);
+        else
+            fsc::launch_negacyclic_mul(d, reinterpret_cast<const int64_t*>(d + bytes / 8), d + 2 * (bytes / 8), (int)count, e->stream);
         ++e->launches;
         err = cudaGetLastError();
     }

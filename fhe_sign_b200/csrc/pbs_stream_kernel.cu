@@ -1,0 +1,432 @@
+// pbs_stream_kernel.cu — batched programmable bootstrapping for sm_100a (k = 1, N = 2048, l = 1), "stream" form.
+//
+// Same algorithm and data flow as pbs_ring_kernel (two warps per ciphertext, warp p owns GLWE polynomial p; the
+// Fourier GGSW of every CMUX step arrives in a shared-memory ring by TMA bulk copies), rebuilt around ONE 32-point
+// pass routine (pbs_core2.cuh): a CMUX step is a four-trip loop
+//
+//      q = 0: head            -> pass(table 0) -> transpose store
+//      q = 1: transpose load  -> pass(table 1) -> Fourier-domain product (key ring, partner exchange)
+//      q = 2:                    pass(table 2) -> transpose store
+//      q = 3: transpose load  -> pass(table 3) -> twist, rounding, accumulation
+//
+// so the loop body holds one copy of the butterflies instead of four: about 2 000 instructions (32 KB) against
+// 4 700 (75 KB), 2 688 FP64 instructions per warp-step against 3 072 (tangent-form butterflies on every pass).
+// Kernels:
+//   bsk_convert_stream_kernel   standard-domain key -> Fourier domain in the product's consumption order
+//   pbs_stream_kernel<AccT, CTS, NCH>
+//
+// Replaces (concept): tfhe 0.10.0 programmable_bootstrap_lwe_ciphertext (Cargo.lock:482-485), the PBS half of
+// shortint apply_lookup_table behind every operator in src/biguint.rs:110-248.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <type_traits>
+#include <vector>
+#include "pbs_core2.cuh"
+#include "fsc_internal.h"
+#include "tma_ring.cuh"
+
+namespace fsc {
+
+// ---- constant tables (global memory image, copied into shared memory by every CTA) --------------------
+// [0, 16)        pass 0 (forward 1, uniform)          [16, 32)      pass 2 (inverse A, uniform)
+// [32, 544)      pass 1 (forward 2, [ci][lane])       [544, 1056)   pass 3 (inverse B, [ci][lane])
+// [1056, 2080)   twist [pos][lane]
+constexpr int kTabU0 = 0, kTabU2 = 16, kTabL1 = 32, kTabL3 = 544, kTabTwist = 1056, kTabCplx = 2080;
+
+// uniform tables (passes 0 and 2) in the constant bank: FP64 instructions take them as direct operands
+__constant__ cplx c_stab[32];
+template <int BASE>
+struct UniformConsts {
+    __device__ __forceinline__ cplx get(int ci) const { return c_stab[BASE + ci]; }
+};
+
+template <typename AccT>
+static const cplx* stream_tables() {      // device pointer, built once per device and accumulator type
+    static cplx* per_dev[64] = {};
+    int dev = 0;
+    FSC_CUDA_CHECK(cudaGetDevice(&dev));
+    cplx*& d = per_dev[dev & 63];
+    if (!d) {
+        std::vector<cplx> h(kTabCplx);
+        for (int ci = 0; ci < 16; ++ci) {
+            h[kTabU0 + ci] = pass_const(ci, pass_g(0, 0));
+            h[kTabU2 + ci] = pass_const(ci, pass_g(2, 0));
+            for (int l = 0; l < 32; ++l) {
+                h[kTabL1 + ci * 32 + l] = pass_const(ci, pass_g(1, l));
+                h[kTabL3 + ci * 32 + l] = pass_const(ci, pass_g(3, l));
+            }
+        }
+        for (int pos = 0; pos < 32; ++pos)
+            for (int l = 0; l < 32; ++l) h[kTabTwist + pos * 32 + l] = twist_const<AccT>(pos, l);
+        FSC_CUDA_CHECK(cudaMemcpyToSymbol(c_stab, h.data(), 32 * sizeof(cplx)));      // kTabU0, kTabU2
+        FSC_CUDA_CHECK(cudaMalloc(&d, kTabCplx * sizeof(cplx)));
+        FSC_CUDA_CHECK(cudaMemcpy(d, h.data(), kTabCplx * sizeof(cplx), cudaMemcpyHostToDevice));
+    }
+    return d;
+}
+
+__device__ __forceinline__ StridedConsts pass_table(const cplx* tabs, int q, int lane) {
+    // q = 0, 2: uniform tables at 0 and 16;  q = 1, 3: per-lane tables at 32 and 544
+    StridedConsts c;
+    c.base = tabs + ((q & 1) ? (q == 1 ? kTabL1 : kTabL3) + lane : (q == 0 ? kTabU0 : kTabU2));
+    c.stride = (q & 1) ? 32 : 1;
+    return c;
+}
+
+// forward FFT of the 32 x 32 complex points held by the warp through the shared pass (tables in global memory)
+__device__ __forceinline__ void stream_fft_fwd(int lane, double* xb, const cplx* tabs, cplx (&v)[32]) {
+    pass32(v, pass_table(tabs, 0, lane));
+    xp_store(lane, xb, v, 0);
+    __syncwarp();
+    xp_load(lane, xb, v, 0);
+    __syncwarp();
+    xp_store(lane, xb, v, 1);
+    __syncwarp();
+    xp_load(lane, xb, v, 1);
+    __syncwarp();
+    pass32(v, pass_table(tabs, 1, lane));
+}
+
+// ---------------------------------------------------------------------------------------
+// Bootstrapping key conversion.  grid = n * 4 polynomials, block = 32.
+// in : bsk [n][p][l=1][q][2048] u64 (standard domain)      out: [n][position][g = 2p+q][lane] cplx
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) bsk_convert_stream_kernel(const uint64_t* __restrict__ bsk, cplx* __restrict__ out,
+                                                                const cplx* __restrict__ tabs) {
+    __shared__ double xb[kXBufDoubles];
+    const int lane = threadIdx.x;
+    const int i = blockIdx.x >> 2, g = blockIdx.x & 3;
+    const uint64_t* src = bsk + (size_t)blockIdx.x * kN;
+    cplx v[32];
+#pragma unroll
+    for (int j2 = 0; j2 < 32; ++j2) {
+        v[j2].x = (double)(int64_t)src[lane + 32 * j2];
+        v[j2].y = (double)(int64_t)src[lane + 32 * j2 + 1024];
+    }
+    stream_fft_fwd(lane, xb, tabs, v);
+#pragma unroll
+    for (int s = 0; s < 32; ++s) out[(((size_t)i * 32 + slot_position(s)) * 4 + g) * 32 + lane] = v[s];
+}
+
+// ---------------------------------------------------------------------------------------
+// Blind rotation + sample extraction.  One CTA = CTS ciphertexts, two warps each.
+// shared memory: acc [CTS][2][1024] pair_t<AccT> | xbuf [CTS][2][1056] double | ring [NCH][512] cplx |
+//                tables [2080] cplx | full[NCH], empty[NCH] mbarriers | prog[CTS]
+// `mode`: > 0 start offset of ciphertext k by k * mode cycles; < 0 chain mode (ciphertext k starts a step after
+// ciphertext k-1 has finished the head of that step); 0 none.
+// ---------------------------------------------------------------------------------------
+template <typename AccT, int CTS, int NCH>
+__global__ void __launch_bounds__(CTS * 64, 1) pbs_stream_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
+                                                                  int n, int base_log, const uint64_t* __restrict__ luts,
+                                                                  const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
+                                                                  const int32_t* __restrict__ out_idx, int count,
+                                                                  const cplx* __restrict__ tabs_g, int mode, long long* dbg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    pair_t<AccT>* acc_all = reinterpret_cast<pair_t<AccT>*>(smem_raw);
+    double* xbuf_all = reinterpret_cast<double*>(smem_raw + (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>));
+    cplx* ring = reinterpret_cast<cplx*>(xbuf_all + (size_t)CTS * 2 * kXBufDoubles);
+    cplx* tabs = ring + (size_t)NCH * kChunkCplx;
+    uint64_t* full = reinterpret_cast<uint64_t*>(tabs + kTabCplx);
+    uint64_t* empty = full + NCH;
+    volatile int* prog = reinterpret_cast<volatile int*>(empty + NCH);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chain = mode < 0 ? -mode : 0;      // 1: full chain; 2: ct 2,3 trail ct 0 by one head; 4: by head + first pass
+    constexpr bool kWholeStep = NCH >= kChunksPerStep;      // the ring holds a whole step's key
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NCH; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 2 * CTS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < CTS) prog[threadIdx.x] = 0;
+    for (int t = threadIdx.x; t < kTabCplx; t += CTS * 64) {
+        const double2 d = __ldg(reinterpret_cast<const double2*>(tabs_g + t));
+        tabs[t].x = d.x; tabs[t].y = d.y;
+    }
+    __syncthreads();
+
+    const int total_chunks = n * kChunksPerStep;
+    const bool producer = warp == 0;                   // warp-uniform
+    RingProducer<NCH> prod;
+    prod.init();
+#define FSC_POLL() do { if (producer) prod.poll(lane, bsk_f, ring, full, empty, total_chunks); } while (0)
+    FSC_POLL();
+
+    const int ctl = warp >> 1, p = warp & 1;
+    const int c_raw = blockIdx.x * CTS + ctl;
+    const bool live = c_raw < count;
+    const int c = live ? c_raw : count - 1;            // padding warps shadow the last ciphertext, never store
+    pair_t<AccT>* acc = acc_all + (size_t)(ctl * 2 + p) * 1024;
+    double* xb = xbuf_all + (size_t)(ctl * 2 + p) * kXBufDoubles;
+    cplx* xc = reinterpret_cast<cplx*>(xb);                                                            // exchange view: [16][32] cplx
+    const cplx* xother = reinterpret_cast<const cplx*>(xbuf_all + (size_t)(ctl * 2 + (1 - p)) * kXBufDoubles);
+    const uint64_t* ct = in_small + (size_t)c * (n + 1);
+    const uint64_t* lut = luts + (size_t)(lut_idx ? lut_idx[c] : 0) * kN;
+    {
+        const int b = modswitch(ct[n]);
+#pragma unroll 4
+        for (int j2 = 0; j2 < 32; ++j2) {
+            const int idx = lane + 32 * j2;
+            pair_t<AccT> z; z.x = 0; z.y = 0;
+            acc[idx] = p ? lut_pair<AccT>(lut, idx, b) : z;
+        }
+    }
+    __syncwarp();
+    if (mode > 0 && ctl > 0) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < (long long)ctl * mode) { }
+        __syncwarp();
+    }
+
+    // Fourier-domain product of this warp: X_p <- X_p * G[p][p] + X_{1-p} * G[1-p][p]  (g = 2 row + col)
+    const int g_own = 3 * p, g_oth = 2 - p;
+    const int row_inv = (32 - lane) & 31;
+    const StridedConsts tab1{tabs + kTabL1 + lane, 32}, tab3{tabs + kTabL3 + lane, 32};
+    int a_chunk = 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    cplx X[32];
+    for (int i = 0; i < n; ++i) {
+        if ((i & 31) == 0) a_chunk = (i + lane < n) ? modswitch(ct[i + lane]) : 0;
+        const int a = __shfl_sync(0xffffffffu, a_chunk, i & 31);
+        if (chain == 1 && ctl > 0) { while (prog[ctl - 1] <= i) { } }
+        if (chain >= 2 && ctl >= 2) { while (prog[0] <= i) { } }
+        if (dbg && lane == 0 && blockIdx.x < 4 && (i & 127) == 0) dbg[(blockIdx.x * 16 + warp) * 8 + (i >> 7)] = clock64();
+
+        // ---- quarter 0: head -> pass (uniform table, constant bank) -> transpose store
+        cmux_head<AccT>(lane, acc, a, base_log, X);
+        if (chain && chain < 4 && p == 0 && lane == 0) prog[ctl] = i + 1;
+        pass32(X, UniformConsts<0>());
+        if (chain == 4 && p == 0 && lane == 0) prog[ctl] = i + 1;
+        xp_store(lane, xb, X, 0);
+        __syncwarp();
+
+        // ---- quarter 1: transpose load -> pass (per-lane table) -> Fourier-domain product
+        xp_load(lane, xb, X, 0);
+        __syncwarp();
+        xp_store(lane, xb, X, 1);
+        __syncwarp();
+        xp_load(lane, xb, X, 1);
+        __syncwarp();
+        pass32(X, tab1);
+        if constexpr (kWholeStep) {
+            // Every chunk of this step must have been requested before any warp may sleep on it.  The producer warp
+            // makes sure of that here, once per step; it cannot deadlock: the stages it waits for are released by
+            // the other warps in the product of the previous step, which never waits for warp 0.
+            if (producer) {
+                while (prod.next_u < (i + 1) * kChunksPerStep && prod.next_u < total_chunks)
+                    prod.poll(lane, bsk_f, ring, full, empty, total_chunks);
+            }
+            // the ring holds the whole step: wait for the four chunks of a half, then one straight-line block of
+            // 48 shared-memory loads and 128 FMAs that the scheduler is free to interleave
+            auto half = [&](auto hc) {
+                constexpr int H = decltype(hc)::value;
+#pragma unroll
+                for (int s = 0; s < 32; ++s)
+                    if ((slot_position(s) >> 4) == H) xc[(slot_position(s) & 15) * 32 + lane] = X[s];
+                pair_barrier(1 + ctl);
+                int st[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    st[k] = stage;
+                    mbar_wait(full + stage, phase);
+                    if (++stage == NCH) { stage = 0; phase ^= 1; }
+                }
+                auto chunk = [&](auto kc) {
+                    constexpr int K = decltype(kc)::value;
+                    cplx o[4], gw[4], go[4];
+                    const cplx* g = ring + (size_t)st[K] * kChunkCplx + lane;
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        o[rr] = xother[(K * 4 + rr) * 32 + lane];
+                        gw[rr] = g[(rr * 4 + g_own) * 32];
+                        go[rr] = g[(rr * 4 + g_oth) * 32];
+                    }
+                    mac_chunk<H * 16 + K * 4>(X, o, gw, go);
+                };
+                chunk(std::integral_constant<int, 0>{});
+                chunk(std::integral_constant<int, 1>{});
+                chunk(std::integral_constant<int, 2>{});
+                chunk(std::integral_constant<int, 3>{});
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) mbar_arrive(empty + st[k]);
+                }
+                pair_barrier(1 + ctl);
+            };
+            half(std::integral_constant<int, 0>{});
+            half(std::integral_constant<int, 1>{});
+        } else {
+            auto chunk = [&](auto r0c) {
+                constexpr int R0 = decltype(r0c)::value;
+                cplx o[4], gw[4], go[4];
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) o[rr] = xother[((R0 + rr) & 15) * 32 + lane];
+                if (producer) {
+                    // ring shorter than a step: the producer must not sleep on a chunk it has not requested yet
+                    while (!mbar_test(full + stage, phase)) prod.poll(lane, bsk_f, ring, full, empty, total_chunks);
+                } else {
+                    mbar_wait(full + stage, phase);
+                }
+                const cplx* g = ring + (size_t)stage * kChunkCplx + lane;
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) { gw[rr] = g[(rr * 4 + g_own) * 32]; go[rr] = g[(rr * 4 + g_oth) * 32]; }
+                mac_chunk<R0>(X, o, gw, go);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + stage);
+                if (++stage == NCH) { stage = 0; phase ^= 1; }
+                FSC_POLL();
+            };
+#pragma unroll
+            for (int s = 0; s < 32; ++s)
+                if (slot_position(s) < 16) xc[slot_position(s) * 32 + lane] = X[s];
+            pair_barrier(1 + ctl);
+            chunk(std::integral_constant<int, 0>{});
+            chunk(std::integral_constant<int, 4>{});
+            chunk(std::integral_constant<int, 8>{});
+            chunk(std::integral_constant<int, 12>{});
+            pair_barrier(1 + ctl);
+#pragma unroll
+            for (int s = 0; s < 32; ++s)
+                if (slot_position(s) >= 16) xc[(slot_position(s) - 16) * 32 + lane] = X[s];
+            pair_barrier(1 + ctl);
+            chunk(std::integral_constant<int, 16>{});
+            chunk(std::integral_constant<int, 20>{});
+            chunk(std::integral_constant<int, 24>{});
+            chunk(std::integral_constant<int, 28>{});
+            pair_barrier(1 + ctl);
+        }
+
+        // ---- quarter 2: pass (uniform table) -> transpose store
+        pass32(X, UniformConsts<16>());
+        xp_store(lane, xb, X, 0);
+        __syncwarp();
+
+        // ---- quarter 3: transpose load -> pass (per-lane table) -> twist, rounding, accumulation
+        xp_load(row_inv, xb, X, 0);
+        __syncwarp();
+        xp_store(lane, xb, X, 1);
+        __syncwarp();
+        xp_load(row_inv, xb, X, 1);
+        __syncwarp();
+        pass32(X, tab3);
+        stream_tail<AccT>(lane, acc, tabs + kTabTwist, X);
+        __syncwarp();
+        FSC_POLL();
+    }
+#undef FSC_POLL
+    pair_barrier(1 + ctl);
+
+    if (live) {
+        uint64_t* out = out_big + (size_t)(out_idx ? out_idx[c] : c) * (kN + 1);
+        const pair_t<AccT>* mask = acc_all + (size_t)(ctl * 2) * 1024;
+        for (int j = (p * 32 + lane); j <= kN; j += 64) out[j] = extract_word<AccT>(mask, mask + 1024, j);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Test hook: c = a (torus) * b (small integers), negacyclic, through the stream FFT.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) negacyclic_mul_stream_kernel(const uint64_t* __restrict__ a, const int64_t* __restrict__ b,
+                                                                   uint64_t* __restrict__ c, const cplx* __restrict__ tabs) {
+    __shared__ double xb[kXBufDoubles];
+    __shared__ pair_t<uint64_t> acc[1024];
+    const int lane = threadIdx.x;
+    a += (size_t)blockIdx.x * kN; b += (size_t)blockIdx.x * kN; c += (size_t)blockIdx.x * kN;
+    cplx va[32], vb[32];
+#pragma unroll
+    for (int j2 = 0; j2 < 32; ++j2) {
+        va[j2].x = (double)(int64_t)a[lane + 32 * j2]; va[j2].y = (double)(int64_t)a[lane + 32 * j2 + 1024];
+        vb[j2].x = (double)b[lane + 32 * j2];          vb[j2].y = (double)b[lane + 32 * j2 + 1024];
+        acc[lane + 32 * j2].x = 0; acc[lane + 32 * j2].y = 0;
+    }
+    stream_fft_fwd(lane, xb, tabs, va);
+    __syncwarp();
+    stream_fft_fwd(lane, xb, tabs, vb);
+    __syncwarp();
+    cplx pr[32];
+#pragma unroll
+    for (int s = 0; s < 32; ++s) {      // slot s holds k1 = brev5(s): the product goes to slot k1
+        const cplx x = va[s], y = vb[s];
+        pr[brev5(s)].x = x.x * y.x - x.y * y.y; pr[brev5(s)].y = x.x * y.y + x.y * y.x;
+    }
+    pass32(pr, pass_table(tabs, 2, lane));
+    xp_store(lane, xb, pr, 0);
+    __syncwarp();
+    xp_load((32 - lane) & 31, xb, pr, 0);
+    __syncwarp();
+    xp_store(lane, xb, pr, 1);
+    __syncwarp();
+    xp_load((32 - lane) & 31, xb, pr, 1);
+    __syncwarp();
+    pass32(pr, pass_table(tabs, 3, lane));
+    stream_tail<uint64_t>(lane, acc, tabs + kTabTwist, pr);
+    __syncwarp();
+#pragma unroll
+    for (int j2 = 0; j2 < 32; ++j2) { c[lane + 32 * j2] = acc[lane + 32 * j2].x; c[lane + 32 * j2 + 1024] = acc[lane + 32 * j2].y; }
+}
+
+// ---------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------
+void launch_bsk_convert_stream(const uint64_t* bsk, void* out, int n, cudaStream_t st) {
+    bsk_convert_stream_kernel<<<n * 4, 32, 0, st>>>(bsk, reinterpret_cast<cplx*>(out), stream_tables<uint64_t>());
+}
+
+void launch_negacyclic_mul_stream(const uint64_t* a, const int64_t* b, uint64_t* c, int count, cudaStream_t st) {
+    negacyclic_mul_stream_kernel<<<count, 32, 0, st>>>(a, b, c, stream_tables<uint64_t>());
+}
+
+template <typename AccT, int CTS, int NCH>
+static void launch_pbs_stream_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
+                                const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
+    const size_t smem = (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>) + (size_t)CTS * 2 * kXBufDoubles * sizeof(double) +
+                        (size_t)NCH * kChunkCplx * sizeof(cplx) + (size_t)kTabCplx * sizeof(cplx) + 2 * NCH * sizeof(uint64_t) + 16;
+    static bool configured = false;
+    if (!configured) {
+        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_stream_kernel<AccT, CTS, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    static int mode = 1 << 30;
+    if (mode == 1 << 30) { const char* e = getenv("FSC_PBS_STAGGER"); mode = e ? atoi(e) : 0; }
+    const int grid = (count + CTS - 1) / CTS;
+    static long long* dbg = nullptr;
+    if (!dbg && getenv("FSC_PBS_DEBUG_CLOCKS")) { FSC_CUDA_CHECK(cudaMalloc(&dbg, 4 * 16 * 8 * 8)); FSC_CUDA_CHECK(cudaMemset(dbg, 0, 4 * 16 * 8 * 8)); }
+    pbs_stream_kernel<AccT, CTS, NCH><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts,
+                                                                     lut_idx, out_big, out_idx, count, stream_tables<AccT>(), mode, dbg);
+    if (dbg) {
+        long long h[4 * 16 * 8];
+        FSC_CUDA_CHECK(cudaStreamSynchronize(st));
+        FSC_CUDA_CHECK(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        for (int b = 0; b < 2; ++b)
+            for (int k = 0; k < 7; ++k) {
+                fprintf(stderr, "block %d step %4d:", b, k * 128);
+                for (int w = 0; w < CTS * 2; ++w) fprintf(stderr, " %8lld", h[(b * 16 + w) * 8 + k] - h[(b * 16) * 8 + k]);
+                fprintf(stderr, "   (step time %lld)\n", k ? (h[(b * 16) * 8 + k] - h[(b * 16) * 8 + k - 1]) / 128 : 0);
+            }
+    }
+}
+
+// Configuration by batch width: wide levels pack 4 (u32 accumulator) or 3 (u64) ciphertexts per CTA so that one key
+// chunk feeds them all; levels of at most one or two ciphertexts per SM use 1 or 2 per CTA (the latency-bound case of
+// the carry-propagation levels: a less contended SM per ciphertext).
+void launch_pbs_stream(int acc_bits, const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
+                       const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, int sm_count, cudaStream_t st) {
+    if (count <= 0) return;
+#define FSC_STREAM(ACC, CTS, NCH) \
+    launch_pbs_stream_t<ACC, CTS, NCH>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st)
+    if (acc_bits == 32) {
+        if (count <= sm_count) FSC_STREAM(uint32_t, 1, 10);
+        else if (count <= 2 * sm_count) FSC_STREAM(uint32_t, 2, 10);
+        else FSC_STREAM(uint32_t, 4, 8);
+    } else {
+        if (count <= sm_count) FSC_STREAM(uint64_t, 1, 10);
+        else if (count <= 2 * sm_count) FSC_STREAM(uint64_t, 2, 10);
+        else FSC_STREAM(uint64_t, 3, 5);
+    }
+#undef FSC_STREAM
+}
+
+}  // namespace fsc

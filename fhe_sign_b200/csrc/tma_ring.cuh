@@ -1,0 +1,84 @@
+// tma_ring.cuh — shared-memory ring fed by 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx): the PTX
+// wrappers and the non-blocking producer used by the blind-rotation kernels to stream the Fourier bootstrapping key.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pbs_core.cuh"
+
+namespace fsc {
+
+constexpr int kChunkSlots = 4;                         // frequency slots per ring chunk
+constexpr int kChunkCplx = kChunkSlots * 4 * 32;       // 512 complex = 8 KiB
+constexpr int kChunksPerStep = 32 / kChunkSlots;       // 8
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void pair_barrier(int id) {      // the two warps of one ciphertext
+    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
+// same with immediate barrier ids, so that ptxas reserves CTS + 1 named barriers instead of all 16 (two CTAs per SM)
+template <int CTS>
+__device__ __forceinline__ void pair_barrier_imm(int ctl) {
+    if (CTS == 1 || ctl == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+    else if (CTS == 2 || ctl == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
+    else if (CTS == 3 || ctl == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
+    else asm volatile("bar.sync 4, 64;" ::: "memory");
+}
+
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// Producer state is kept by every lane of warp 0 and advanced with warp-uniform control flow (the barrier test reads
+// one address, so all lanes agree); only the two issue instructions are predicated on lane 0.  A producer that
+// diverges from its warp makes that warp - a consumer like the others - run whole phases twice.
+template <int NCH>
+struct RingProducer {
+    int next_u, stage;
+    uint32_t phase;            // parity of the `empty` phase that frees `stage`
+    __device__ __forceinline__ void init() { next_u = 0; stage = 0; phase = 1; }      // phase 1: "previous" phase of a fresh barrier
+    __device__ __forceinline__ void poll(int lane, const cplx* bsk_f, cplx* ring, uint64_t* full, uint64_t* empty, int total_chunks) {
+        while (next_u < total_chunks) {
+            if (!mbar_test(empty + stage, phase)) break;
+            if (lane == 0) {
+                mbar_arrive_expect_tx(full + stage, kChunkCplx * sizeof(cplx));
+                bulk_load(ring + (size_t)stage * kChunkCplx, bsk_f + (size_t)next_u * kChunkCplx, kChunkCplx * sizeof(cplx), full + stage);
+            }
+            __syncwarp();
+            ++next_u;
+            if (++stage == NCH) { stage = 0; phase ^= 1; }
+        }
+    }
+};
+
+}  // namespace fsc

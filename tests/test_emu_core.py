@@ -58,3 +58,65 @@ def test_emu_blind_rotation_decrypts_like_oracle(emu, orc, oracle_keys, rng, acc
     e_emu = (K.phase_big(out) - K.encode(table[m])).astype(np.int64).astype(np.float64)
     e_ref = (K.phase_big(ref) - K.encode(table[m])).astype(np.int64).astype(np.float64)
     assert e_emu.std() < 1.5 * e_ref.std()
+
+
+# ---- the single-routine "stream" formulation (pbs_core2.cuh / pbs_stream_kernel.cu) ----
+
+@pytest.fixture(scope="module")
+def emu2():
+    so = os.path.join(HERE, "emu", "libpbs_emu2.so")
+    src = os.path.join(HERE, "emu", "pbs_emu2.cpp")
+    cores = [os.path.join(HERE, "..", "fhe_sign_b200", "csrc", f) for f in ("pbs_core.cuh", "pbs_core2.cuh")]
+    if not os.path.exists(so) or max([os.path.getmtime(src)] + [os.path.getmtime(c) for c in cores]) > os.path.getmtime(so):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-march=x86-64-v3", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
+    E = C.CDLL(so)
+    vp = C.c_void_p
+    E.emu2_negacyclic_mul.argtypes = [vp, vp, vp]
+    E.emu2_convert_bsk.argtypes = [C.c_int, vp, vp]
+    E.emu2_blind_rotate.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
+    E.emu2_min_cos.restype = C.c_double
+    return E
+
+
+def test_stream_frequency_order_is_closed_under_bit_reversal():
+    """pbs_core2.cuh freq_at / freq_pos: halves and 4-slot chunks closed under brev5 (the product swaps slots inside a chunk)."""
+    def brev5(v):
+        return ((v & 1) << 4) | ((v & 2) << 2) | (v & 4) | ((v & 8) >> 2) | ((v & 16) >> 4)
+    seq = [0, 2, 8, 4, 6, 12, 10, 14, 17, 19, 25, 21, 23, 29, 27, 31, 1, 16, 3, 24, 5, 20, 7, 28, 9, 18, 11, 26, 13, 22, 15, 30]
+    pos = [0, 16, 1, 18, 3, 20, 4, 22, 2, 24, 6, 26, 5, 28, 7, 30, 17, 8, 25, 9, 21, 11, 29, 12, 19, 10, 27, 14, 23, 13, 31, 15]
+    assert sorted(seq) == list(range(32)) and all(pos[k] == seq.index(k) for k in range(32))
+    for c in range(8):
+        chunk = seq[4 * c:4 * c + 4]
+        assert sorted(chunk) == sorted(brev5(x) for x in chunk)
+
+
+def test_stream_tangent_constants_are_finite(emu2):
+    assert emu2.emu2_min_cos() > 4e-3
+
+
+def test_stream_fft_matches_exact_product(emu2, orc, rng):
+    a = rng.integers(0, 2**64, 2048, dtype=np.uint64)
+    b = rng.integers(-2**22, 2**22, 2048, dtype=np.int64)
+    c = np.empty_like(a)
+    emu2.emu2_negacyclic_mul(P(a), P(b), P(c))
+    d = (c - orc.negacyclic_mul_exact(a, b)).astype(np.int64)
+    assert np.abs(d).max() < 2**43
+
+
+@pytest.mark.parametrize("acc_bits", [64, 32])
+def test_stream_blind_rotation_decrypts_like_oracle(emu2, orc, oracle_keys, rng, acc_bits):
+    K = oracle_keys("toy")
+    n = K.params.lwe_dim
+    bf = np.empty(n * 32 * 4 * 32 * 2, dtype=np.float64)
+    emu2.emu2_convert_bsk(n, P(K.bsk), P(bf))
+    table = rng.integers(0, 16, 16).astype(np.uint64)
+    lut = K.make_lut(table)
+    m = rng.integers(0, 16, 48).astype(np.uint64)
+    small = K.keyswitch(K.encrypt_msgs(m))
+    out = np.empty((m.size, 2049), dtype=np.uint64)
+    emu2.emu2_blind_rotate(acc_bits, n, K.params.pbs_base_log, P(bf), P(small), m.size, P(lut), P(out))
+    ref = K.pbs(small, lut)
+    assert (K.decrypt_msgs(out) == table[m]).all()
+    e_emu = (K.phase_big(out) - K.encode(table[m])).astype(np.int64).astype(np.float64)
+    e_ref = (K.phase_big(ref) - K.encode(table[m])).astype(np.int64).astype(np.float64)
+    assert e_emu.std() < 1.5 * e_ref.std()
