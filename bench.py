@@ -29,6 +29,10 @@ ACC_BITS = int(os.environ.get("FSC_BENCH_ACC_BITS", "32"))
 WORKLOAD = "batched PBS microbench: %d LWE blocks, PARAM_MESSAGE_2_CARRY_2 (%s), keyswitch+PBS per block" % (BATCH, PRESET)
 
 
+# DRAM bytes (read + write) of one 4096-block launch, from the ncu --set full captures summarised in profiles/
+NCU_TRAFFIC = {"pbs_ring_kernel": 252.07e6, "pbs_stream_kernel": None}
+
+
 def flops_per_pbs(n, N=2048, k=1, l=1):
     """n * [((k+1)l + (k+1)) * (5 M log2 M + 6 M) + 8 (k+1)^2 l M], M = N/2."""
     M = N // 2
@@ -233,6 +237,7 @@ def main():
         ms_step = ms_total / args.steps
         value = world * BATCH * args.steps / (ms_total * 1e-3)
         F = flops_per_pbs(n)
+        kernel_name = ctx.pbs_kernel_name()
         achieved_tf = BATCH * F / (ms_pbs * 1e-3) / 1e12
         hbm_bytes = BATCH * (n + 1) * 8 + BATCH * words * 8 + n * 65536     # small LWE in, big LWE out, Fourier BSK once
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
@@ -245,9 +250,9 @@ def main():
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_peak if fp64_peak else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one 4096-block launch, ncu --set full capture
-                         # profiles/r01_ncu_key_metrics.json (pbs_ring_kernel, n=834, acc 32): 191.8 MB + 60.3 MB
-                         "traffic": 252.07e6 if (BATCH == 4096 and n == 834 and ACC_BITS == 32) else None,
-                         "kernel": "pbs_ring_kernel", "ms_per_launch": ms_pbs, "flops_per_pbs": F,
+                         # (profiles/r01_ncu_key_metrics.json, n=834, acc 32)
+                         "traffic": NCU_TRAFFIC.get(kernel_name) if (BATCH == 4096 and n == 834 and ACC_BITS == 32) else None,
+                         "kernel": kernel_name, "ms_per_launch": ms_pbs, "flops_per_pbs": F,
                          "peak_source": "measured in this run (fsc_measure_fp64_peak; MEASURED_PEAKS.json has no FP64 figure)",
                          "keyswitch_ms_per_launch": ms_ks,
                          "hbm": {"achieved": hbm_bytes / (ms_pbs * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

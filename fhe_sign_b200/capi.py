@@ -85,6 +85,8 @@ def load_library():
         f.restype = i32
     L.fsc_last_error.argtypes = [vp]
     L.fsc_last_error.restype = C.c_char_p
+    L.fsc_pbs_kernel_name.argtypes = [vp]
+    L.fsc_pbs_kernel_name.restype = C.c_char_p
     _LIB = L
     return L
 
@@ -93,7 +95,7 @@ EXPORTS = ["fsc_ctx_create", "fsc_ctx_destroy", "fsc_last_error", "fsc_get_param
            "fsc_lwe_alloc", "fsc_lwe_free", "fsc_lwe_upload", "fsc_lwe_download", "fsc_lwe_info",
            "fsc_luts_from_tables", "fsc_luts_upload", "fsc_luts_free", "fsc_keyswitch_batch", "fsc_pbs_batch",
            "fsc_ks_pbs_batch", "fsc_apply_lut_host", "fsc_timer_start", "fsc_timer_stop", "fsc_launch_count",
-           "fsc_debug_negacyclic_mul", "fsc_measure_fp64_peak"]
+           "fsc_debug_negacyclic_mul", "fsc_measure_fp64_peak", "fsc_pbs_kernel_name"]
 from .radix import RADIX_EXPORTS  # noqa: E402
 EXPORTS = EXPORTS + RADIX_EXPORTS + ["fsc_client_keygen", "fsc_client_free", "fsc_client_last_error", "fsc_client_server_keys",
                                      "fsc_client_secret_keys", "fsc_client_encrypt_blocks", "fsc_client_decrypt_blocks"]
@@ -246,6 +248,9 @@ class Context:
         n = C.c_uint64()
         self.L.fsc_launch_count(self.h, C.byref(n))
         return n.value
+
+    def pbs_kernel_name(self):
+        return self.L.fsc_pbs_kernel_name(self.h).decode()
 
     def measure_fp64_peak(self):
         t = C.c_double()

@@ -95,7 +95,8 @@ void Engine::upload_keys(const uint64_t* bsk_std, size_t bsk_words, const uint64
     if (e != cudaSuccess) { cudaFree(tmp); FSC_CUDA_CHECK(e); }
     FSC_CUDA_CHECK(cudaMemcpyAsync(tmp, bsk_std, want_bsk * 8, cudaMemcpyHostToDevice, stream));
     FSC_CUDA_CHECK(cudaMemcpyAsync(ksk, ksk_h, want_ksk * 8, cudaMemcpyHostToDevice, stream));
-    if (pbs_variant() == 2) launch_bsk_convert_stream(tmp, bsk_f, (int)n, stream);      // the stream kernel's key order
+    pbs_variant = pbs_variant_for((int)p.acc_bits);
+    if (pbs_variant == 2) launch_bsk_convert_stream(tmp, bsk_f, (int)n, stream);      // the stream kernel's key order
     else launch_bsk_convert(tmp, bsk_f, (int)n, stream);
     ++launches;
     FSC_CUDA_CHECK(cudaGetLastError());
@@ -175,11 +176,11 @@ void Engine::pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut
                  const int32_t* out_idx_dev) {
     use();
     if (!bsk_f) throw Error(FSC_ERR_NO_KEYS, "server keys not uploaded");
-    if (pbs_variant() == 2)
+    if (pbs_variant == 2)
         launch_pbs_stream((int)p.acc_bits, bsk_f, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, out_big,
                           out_idx_dev, (int)count, sm_count, stream);
     else
-        launch_pbs((int)p.acc_bits, bsk_f, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, out_big,
+        launch_pbs(pbs_variant, (int)p.acc_bits, bsk_f, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, out_big,
                    out_idx_dev, (int)count, sm_count, stream);
     ++launches;
     FSC_CUDA_CHECK(cudaGetLastError());
@@ -470,6 +471,12 @@ fsc_status fsc_launch_count(const fsc_ctx* ctx, uint64_t* out) {
     return FSC_OK;
 }
 
+const char* fsc_pbs_kernel_name(const fsc_ctx* ctx) {
+    if (!ctx) return "";
+    const int v = ctx->eng->bsk_f ? ctx->eng->pbs_variant : fsc::pbs_variant_for((int)ctx->eng->p.acc_bits);
+    return v == 2 ? "pbs_stream_kernel" : v == 1 ? "pbs_ring_kernel" : "pbs_pair_kernel";
+}
+
 fsc_status fsc_measure_fp64_peak(fsc_ctx* ctx, double* tflops) {
     FSC_API_BEGIN(ctx)
     FSC_REQUIRE(tflops, "null argument");
@@ -507,7 +514,7 @@ fsc_status fsc_debug_negacyclic_mul(fsc_ctx* ctx, const uint64_t* a, const int64
     cudaError_t err = cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, e->stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(d + bytes / 8, b, bytes, cudaMemcpyHostToDevice, e->stream);
     if (err == cudaSuccess) {
-        if (fsc::pbs_variant() == 2)
+        if (fsc::pbs_variant_for((int)e->p.acc_bits) == 2)
             fsc::launch_negacyclic_mul_stream(d, reinterpret_cast<const int64_t*>(d + bytes / 8), d + 2 * (bytes / 8), (int)count, e->stream);
         else
             fsc::launch_negacyclic_mul(d, reinterpret_cast<const int64_t*>(d + bytes / 8), d + 2 * (bytes / 8), (int)count, e->stream);

@@ -30,7 +30,7 @@ struct Error : std::runtime_error {
 // pbs_kernel.cu
 void pbs_init_constants();
 void launch_bsk_convert(const uint64_t* bsk_std, void* bsk_fourier, int n, cudaStream_t st);
-void launch_pbs(int acc_bits, const void* bsk_fourier, const uint64_t* in_small, int n, int base_log,
+void launch_pbs(int variant, int acc_bits, const void* bsk_fourier, const uint64_t* in_small, int n, int base_log,
                 const uint64_t* luts, const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count,
                 int sm_count, cudaStream_t st);
 void launch_negacyclic_mul(const uint64_t* a, const int64_t* b, uint64_t* c, int count, cudaStream_t st);
@@ -41,8 +41,8 @@ void launch_pbs_stream(int acc_bits, const void* bsk_fourier, const uint64_t* in
                        const uint64_t* luts, const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count,
                        int sm_count, cudaStream_t st);
 void launch_negacyclic_mul_stream(const uint64_t* a, const int64_t* b, uint64_t* c, int count, cudaStream_t st);
-// 0: pair, 1: ring, 2: stream (FSC_PBS_VARIANT)
-int pbs_variant();
+// 0: pair, 1: ring, 2: stream (FSC_PBS_VARIANT, else by accumulator width); fixed per context at key upload
+int pbs_variant_for(int acc_bits);
 
 double launch_fp64_peak(double* sink, int sm_count, int iters, cudaStream_t st);
 

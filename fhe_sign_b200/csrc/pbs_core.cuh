@@ -374,13 +374,7 @@ FSC_HD double decomp_digit(AccT d, int base_log) {
     typedef typename acc_traits<AccT>::s_t s_t;
     const int sh = acc_traits<AccT>::bits - base_log;
     const AccT r = (AccT)(d + ((AccT)1 << (sh - 1)));
-    const int32_t digit = (int32_t)((s_t)r >> sh);
-#if defined(__CUDA_ARCH__)
-    // int -> double without the quarter-rate conversion unit: the integer goes into the mantissa of 2^52 + 2^31 + digit
-    return __hiloint2double(0x43300000, digit ^ (int32_t)0x80000000) - 4503601774854144.0;
-#else
-    return (double)digit;
-#endif
+    return (double)(int32_t)((s_t)r >> sh);
 }
 
 // head: z[j2] = digit(X^a acc - acc) at folded index lane + 32 j2

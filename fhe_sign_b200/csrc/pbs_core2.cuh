@@ -121,7 +121,7 @@ FSC_HD void xp_load(int row, const double* xb, cplx (&v)[32], int comp) {
 // under brev5), reads its four old slots first and writes the four new ones.
 // o: partner spectrum, gw / go: GGSW entries multiplying the own / the partner spectrum, all in position order.
 template <int R0>
-FSC_HD void mac_chunk(cplx (&X)[32], const cplx (&o)[4], const cplx (&gw)[4], const cplx (&go)[4]) {
+FSC_HD void mac_own(cplx (&X)[32], const cplx (&gw)[4]) {      // own spectrum x own GGSW entry, bit reversal absorbed
     cplx xin[4];
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) xin[rr] = X[brev5(freq_at(R0 + rr))];
@@ -129,10 +129,25 @@ FSC_HD void mac_chunk(cplx (&X)[32], const cplx (&o)[4], const cplx (&gw)[4], co
     for (int rr = 0; rr < 4; ++rr) {
         const cplx x = xin[rr];
         cplx y;
-        y.x = fma(-o[rr].y, go[rr].y, fma(o[rr].x, go[rr].x, fma(-x.y, gw[rr].y, x.x * gw[rr].x)));
-        y.y = fma(o[rr].y, go[rr].x, fma(o[rr].x, go[rr].y, fma(x.y, gw[rr].x, x.x * gw[rr].y)));
+        y.x = fma(-x.y, gw[rr].y, x.x * gw[rr].x);
+        y.y = fma(x.y, gw[rr].x, x.x * gw[rr].y);
         X[freq_at(R0 + rr)] = y;
     }
+}
+template <int R0>
+FSC_HD void mac_oth(cplx (&X)[32], const cplx (&o)[4], const cplx (&go)[4]) {      // + partner spectrum x other entry
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        cplx y = X[freq_at(R0 + rr)];
+        y.x = fma(-o[rr].y, go[rr].y, fma(o[rr].x, go[rr].x, y.x));
+        y.y = fma(o[rr].y, go[rr].x, fma(o[rr].x, go[rr].y, y.y));
+        X[freq_at(R0 + rr)] = y;
+    }
+}
+template <int R0>
+FSC_HD void mac_chunk(cplx (&X)[32], const cplx (&o)[4], const cplx (&gw)[4], const cplx (&go)[4]) {
+    mac_own<R0>(X, gw);
+    mac_oth<R0>(X, o, go);
 }
 // position (0..31) in the consumption order of the frequency held by slot s after forward pass 2
 FSC_HD constexpr int slot_position(int s) { return freq_pos(brev5(s)); }

@@ -383,181 +383,6 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
 }
 
 // ---------------------------------------------------------------------------------------
-// Decoupled ring variant.  Same data flow as pbs_ring_kernel (half-size transposes, per-lane constants in shared
-// memory), but
-//   * the producer never blocks: at poll points spread over the whole CMUX step it tests the `empty` barrier of the
-//     next ring stage and issues every bulk copy whose stage is free, so the key of step i+1 is requested while
-//     step i is still in its FFT phases (a whole step of latency slack instead of a few chunks);
-//   * OCC CTAs of CTS ciphertexts share an SM, each with its own ring: their phases are independent, and a start
-//     offset of (slot * CTS + ctl) * stagger cycles keeps the FP64 phases of one warp of an SM sub-partition over
-//     the shared-memory / integer phases of the other;
-//   * the partner's spectrum is fetched before the ring wait so that the wait hides its latency.
-// shared memory: acc [CTS][2][1024] pair_t<AccT> | xbuf [CTS][2][512] cplx | ring [NCH][512] cplx | s2tab [16][32] cplx |
-//                full[NCH], empty[NCH] mbarriers
-// ---------------------------------------------------------------------------------------
-__device__ unsigned int g_sm_slot[1024];
-
-template <typename AccT, int CTS, int NCH, int OCC>
-__global__ void __launch_bounds__(CTS * 64, OCC) pbs_ring2_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
-                                                                   int n, int base_log, const uint64_t* __restrict__ luts,
-                                                                   const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
-                                                                   const int32_t* __restrict__ out_idx, int count, int stagger) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    pair_t<AccT>* acc_all = reinterpret_cast<pair_t<AccT>*>(smem_raw);
-    cplx* xbuf_all = reinterpret_cast<cplx*>(smem_raw + (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>));
-    cplx* ring = xbuf_all + (size_t)CTS * 2 * 512;
-    cplx* s2tab = ring + (size_t)NCH * kChunkCplx;
-    uint64_t* full = reinterpret_cast<uint64_t*>(s2tab + 16 * 32);
-    uint64_t* empty = full + NCH;
-    volatile int* prog = reinterpret_cast<volatile int*>(empty + NCH);      // [CTS] step tokens of the chain mode
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // stagger < 0 selects the chain mode: ciphertext k of the CTA starts CMUX step i only after ciphertext k-1 has
-    // passed point -stagger of step i (1: head done, 2: forward FFT done, 3: product done).  The ciphertexts then run
-    // the same instruction stream a fixed, small distance apart: the FP64 phases of one overlap the integer and
-    // shared-memory phases of the others while the trailing warps still hit the instruction cache lines the leader
-    // fetched (the loop body is larger than the instruction cache; independent streams thrash it).
-    const int chain = stagger < 0 ? -stagger : 0;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NCH; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 2 * CTS); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (threadIdx.x < CTS) prog[threadIdx.x] = 0;
-    if (warp == 0) {
-        cplx tmp[16];
-        lane_consts_tan(4 * lane + 1, kP2Center, 6, tmp);
-#pragma unroll
-        for (int ci = 0; ci < 16; ++ci) s2tab[ci * 32 + lane] = tmp[ci];
-    }
-    __syncthreads();
-
-    const int total_chunks = n * kChunksPerStep;
-    const bool producer = warp == 0;                   // warp-uniform
-    RingProducer<NCH> prod;
-    prod.init();
-#define FSC_POLL() do { if (producer) prod.poll(lane, bsk_f, ring, full, empty, total_chunks); } while (0)
-    FSC_POLL();
-
-    const int ctl = warp >> 1, p = warp & 1;
-    const int c_raw = blockIdx.x * CTS + ctl;
-    const bool live = c_raw < count;
-    const int c = live ? c_raw : count - 1;            // padding warps shadow the last ciphertext, never store
-    pair_t<AccT>* acc = acc_all + (size_t)(ctl * 2 + p) * 1024;
-    cplx* xbuf = xbuf_all + (size_t)(ctl * 2 + p) * 512;
-    const cplx* xother = xbuf_all + (size_t)(ctl * 2 + (1 - p)) * 512;
-    const uint64_t* ct = in_small + (size_t)c * (n + 1);
-    const uint64_t* lut = luts + (size_t)(lut_idx ? lut_idx[c] : 0) * kN;
-    const SmemLaneConsts c2s{s2tab + lane};
-    {
-        const int b = modswitch(ct[n]);
-#pragma unroll 4
-        for (int j2 = 0; j2 < 32; ++j2) {
-            const int idx = lane + 32 * j2;
-            pair_t<AccT> z; z.x = 0; z.y = 0;
-            acc[idx] = p ? lut_pair<AccT>(lut, idx, b) : z;
-        }
-    }
-    __syncwarp();
-
-    if (stagger > 0) {
-        int slot = 0;
-        if (OCC > 1) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            __shared__ int s_slot;
-            if (threadIdx.x == 0) s_slot = (int)(atomicAdd(&g_sm_slot[smid & 1023], 1u) % (unsigned)OCC);
-            __syncthreads();
-            slot = s_slot;
-        }
-        const int ph = slot * CTS + ctl;
-        if (ph > 0) {
-            const long long t0 = clock64();
-            while (clock64() - t0 < (long long)ph * stagger) { }
-        }
-        __syncwarp();
-    }
-
-    const int g_own = 3 * p, g_oth = 2 - p;
-    int a_chunk = 0;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int i = 0; i < n; ++i) {
-        if ((i & 31) == 0) a_chunk = (i + lane < n) ? modswitch(ct[i + lane]) : 0;
-        const int a = __shfl_sync(0xffffffffu, a_chunk, i & 31);
-
-        if (chain && ctl > 0) { while (prog[ctl - 1] <= i) { } }
-        cplx X[32];
-        cmux_head<AccT>(lane, acc, a, base_log, X);
-        if (chain == 1 && p == 0 && lane == 0) prog[ctl] = i + 1;
-        FSC_POLL();
-        warp_fft_fwd_h<0>(lane, reinterpret_cast<double*>(xbuf), c2s, X);
-        if (chain == 2 && p == 0 && lane == 0) prog[ctl] = i + 1;
-        FSC_POLL();
-
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-#pragma unroll
-            for (int r = 0; r < 16; ++r) xbuf[r * 32 + lane] = X[half * 16 + r];
-            pair_barrier_imm<CTS>(ctl);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                cplx o[kChunkSlots];
-#pragma unroll
-                for (int rr = 0; rr < kChunkSlots; ++rr) o[rr] = xother[(k * kChunkSlots + rr) * 32 + lane];
-                if (producer) {
-                    // the producer must not sleep on a chunk it has not requested yet
-                    while (!mbar_test(full + stage, phase)) prod.poll(lane, bsk_f, ring, full, empty, total_chunks);
-                } else {
-                    mbar_wait(full + stage, phase);
-                }
-                const cplx* g = ring + (size_t)stage * kChunkCplx + lane;
-#pragma unroll
-                for (int rr = 0; rr < kChunkSlots; ++rr) {
-                    const int r = half * 16 + k * kChunkSlots + rr;
-                    const cplx gw = g[(rr * 4 + g_own) * 32], go = g[(rr * 4 + g_oth) * 32];
-                    const cplx x = X[r];
-                    X[r].x = x.x * gw.x - x.y * gw.y + o[rr].x * go.x - o[rr].y * go.y;
-                    X[r].y = x.x * gw.y + x.y * gw.x + o[rr].x * go.y + o[rr].y * go.x;
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty + stage);
-                if (++stage == NCH) { stage = 0; phase ^= 1; }
-                FSC_POLL();
-            }
-            pair_barrier_imm<CTS>(ctl);
-        }
-        if (chain == 3 && p == 0 && lane == 0) prog[ctl] = i + 1;
-
-        dft32_inv_tan<kP2Center, 6>(X, c2s);
-        FSC_POLL();
-        {
-            double* xb = reinterpret_cast<double*>(xbuf);
-            xpose_store_inv_h(lane, xb, X, 0);
-            __syncwarp();
-            xpose_load_inv_h(lane, xb, X, 0);
-            __syncwarp();
-            xpose_store_inv_h(lane, xb, X, 1);
-            __syncwarp();
-            xpose_load_inv_h(lane, xb, X, 1);
-            __syncwarp();
-        }
-        FSC_POLL();
-        dft32_inv(X, S1PlainDev());
-        cmux_tail<AccT>(lane, acc, X);
-        FSC_POLL();
-        __syncwarp();
-    }
-#undef FSC_POLL
-    pair_barrier_imm<CTS>(ctl);
-
-    if (live) {
-        uint64_t* out = out_big + (size_t)(out_idx ? out_idx[c] : c) * (kN + 1);
-        const pair_t<AccT>* mask = acc_all + (size_t)(ctl * 2) * 1024;
-        for (int j = (p * 32 + lane); j <= kN; j += 64) out[j] = extract_word<AccT>(mask, mask + 1024, j);
-    }
-}
-
-// ---------------------------------------------------------------------------------------
 // Test hook: c = a (torus) * b (small integers), negacyclic, through the kernel's own FFT.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) negacyclic_mul_kernel(const uint64_t* __restrict__ a, const int64_t* __restrict__ b,
@@ -627,64 +452,37 @@ static void launch_pbs_ring_t(const void* bsk_f, const uint64_t* in_small, int n
                                                                         luts, lut_idx, out_big, out_idx, count, stagger);
 }
 
-template <typename AccT, int CTS, int NCH, int OCC>
-static void launch_pbs_ring2_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
-                               const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
-    const size_t smem = (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>) + (size_t)CTS * 2 * 512 * sizeof(cplx) +
-                        (size_t)NCH * kChunkCplx * sizeof(cplx) + 16 * 32 * sizeof(cplx) + 2 * NCH * sizeof(uint64_t) + 16;
-    static bool configured = false;
-    if (!configured) {
-        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_ring2_kernel<AccT, CTS, NCH, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_ring2_kernel<AccT, CTS, NCH, OCC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = true;
-    }
-    static int stagger = -1;
-    if (stagger < 0) { const char* e = getenv("FSC_PBS_STAGGER"); stagger = e ? atoi(e) : 0; }
-    const int grid = (count + CTS - 1) / CTS;
-    pbs_ring2_kernel<AccT, CTS, NCH, OCC><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log,
-                                                                         luts, lut_idx, out_big, out_idx, count, stagger);
-}
-
-static int pbs_cfg() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("FSC_PBS_CFG"); v = e ? atoi(e) : 0; }
-    return v;
-}
-int pbs_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("FSC_PBS_VARIANT");      // "pair" (first version) | "ring" | "stream"
-        v = (e && e[0] == 'p') ? 0 : (e && e[0] == 's') ? 2 : 1;
-    }
-    return v;
+// Which blind-rotation kernel a context uses (fixed at key upload, because the Fourier key layout differs):
+// FSC_PBS_VARIANT = "pair" (first version, one ciphertext per CTA) | "ring" | "stream"; default: stream for the 32-bit
+// accumulator, ring for the 64-bit accumulator (three ciphertexts per CTA do not fit beside the stream kernel's
+// whole-step key ring).
+int pbs_variant_for(int acc_bits) {
+    const char* e = getenv("FSC_PBS_VARIANT");
+    if (e && e[0] == 'p') return 0;
+    if (e && e[0] == 'r') return 1;
+    if (e && e[0] == 's') return 2;
+    return acc_bits == 32 ? 2 : 1;
 }
 
 // Ring kernel configuration by batch width: wide levels pack 4 (u32 accumulator) or 3 (u64) ciphertexts per CTA
 // to share every key chunk; narrow levels (at most one or two ciphertexts per SM) use 1 or 2 per CTA so that each
 // ciphertext gets a less contended SM and the whole step's key fits in the ring - that is the latency-bound case
 // of the carry-propagation levels.
-void launch_pbs(int acc_bits, const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
+void launch_pbs(int variant, int acc_bits, const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
                 const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, int sm_count, cudaStream_t st) {
     if (count <= 0) return;
 #define FSC_RING(ACC, CTS, NCH) \
     launch_pbs_ring_t<ACC, CTS, NCH, true, 0>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st)
-    if (pbs_variant() == 0) {
+    if (variant == 0) {
         if (acc_bits == 32) launch_pbs_pair_t<uint32_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
         else launch_pbs_pair_t<uint64_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
-    } else if (acc_bits == 32 && count > 2 * sm_count && pbs_cfg() > 0) {
-#define FSC_RING2(CTS, NCH, OCC) launch_pbs_ring2_t<uint32_t, CTS, NCH, OCC>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st)
-        if (pbs_cfg() == 1) FSC_RING2(4, 11, 1);
-        else FSC_RING2(2, 5, 2);
-#undef FSC_RING2
     } else if (acc_bits == 32) {
         if (count <= sm_count) FSC_RING(uint32_t, 1, 10);
         else if (count <= 2 * sm_count) FSC_RING(uint32_t, 2, 10);
-        else if (getenv("FSC_PBS_FULLBUF")) FSC_RING(uint32_t, 4, 3);      // 16 KiB transpose buffers, 3-chunk ring
         else launch_pbs_ring_t<uint32_t, 4, 11, true, 0, true>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
     } else {
         if (count <= sm_count) FSC_RING(uint64_t, 1, 10);
         else if (count <= 2 * sm_count) FSC_RING(uint64_t, 2, 10);
-        else if (getenv("FSC_PBS_FULLBUF")) FSC_RING(uint64_t, 3, 3);
         else launch_pbs_ring_t<uint64_t, 3, 9, true, 0, true>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
     }
 #undef FSC_RING

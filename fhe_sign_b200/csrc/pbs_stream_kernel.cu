@@ -13,7 +13,7 @@
 // 4 700 (75 KB), 2 688 FP64 instructions per warp-step against 3 072 (tangent-form butterflies on every pass).
 // Kernels:
 //   bsk_convert_stream_kernel   standard-domain key -> Fourier domain in the product's consumption order
-//   pbs_stream_kernel<AccT, CTS, NCH>
+//   pbs_stream_kernel<AccT, CTS, NH>
 //
 // Replaces (concept): tfhe 0.10.0 programmable_bootstrap_lwe_ciphertext (Cargo.lock:482-485), the PBS half of
 // shortint apply_lookup_table behind every operator in src/biguint.rs:110-248.
@@ -21,6 +21,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <type_traits>
 #include <vector>
 #include "pbs_core2.cuh"
@@ -34,13 +35,6 @@ namespace fsc {
 // [32, 544)      pass 1 (forward 2, [ci][lane])       [544, 1056)   pass 3 (inverse B, [ci][lane])
 // [1056, 2080)   twist [pos][lane]
 constexpr int kTabU0 = 0, kTabU2 = 16, kTabL1 = 32, kTabL3 = 544, kTabTwist = 1056, kTabCplx = 2080;
-
-// uniform tables (passes 0 and 2) in the constant bank: FP64 instructions take them as direct operands
-__constant__ cplx c_stab[32];
-template <int BASE>
-struct UniformConsts {
-    __device__ __forceinline__ cplx get(int ci) const { return c_stab[BASE + ci]; }
-};
 
 template <typename AccT>
 static const cplx* stream_tables() {      // device pointer, built once per device and accumulator type
@@ -60,7 +54,6 @@ static const cplx* stream_tables() {      // device pointer, built once per devi
         }
         for (int pos = 0; pos < 32; ++pos)
             for (int l = 0; l < 32; ++l) h[kTabTwist + pos * 32 + l] = twist_const<AccT>(pos, l);
-        FSC_CUDA_CHECK(cudaMemcpyToSymbol(c_stab, h.data(), 32 * sizeof(cplx)));      // kTabU0, kTabU2
         FSC_CUDA_CHECK(cudaMalloc(&d, kTabCplx * sizeof(cplx)));
         FSC_CUDA_CHECK(cudaMemcpy(d, h.data(), kTabCplx * sizeof(cplx), cudaMemcpyHostToDevice));
     }
@@ -89,6 +82,61 @@ __device__ __forceinline__ void stream_fft_fwd(int lane, double* xb, const cplx*
     pass32(v, pass_table(tabs, 1, lane));
 }
 
+// ---- head for the 32-bit accumulator, written for the ALU / FMA pipe split --------------------------------
+// Same result as cmux_head<uint32_t> (pbs_core.cuh).  Over the 32 elements of a lane the rotated index crosses a
+// multiple of 1024 at most once, so the swap / sign configuration of X^a takes two values per lane, A before the
+// crossing and B after it; per element c in {0, 1} blends them with integer multiply-adds (FMA pipe) instead of
+// predicated selects, and the int -> double conversion goes through the mantissa trick instead of the quarter-rate
+// conversion unit.  About 13 ALU + 6 FMA-pipe + 2 FP64 instructions per coefficient pair, no predicates.
+__device__ __forceinline__ int imad(int a, int b, int c) {
+    int d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ void stream_head_u32(int lane, const pair_t<uint32_t>* poly, int a, int base_log, cplx (&z)[32]) {
+    const int sh = 32 - base_log;
+    const int half = 1 << (sh - 1);
+    const int base = (lane - a) & 4095;
+    const int q0 = base >> 10, q1 = (q0 + 1) & 3;
+    // quadrant q: (x, y) <- 0: (+x, +y)  1: (+y, -x)  2: (-x, -y)  3: (-y, +x)
+    const int swA = q0 & 1;
+    const int sxA = 1 - (q0 & 2), syA = 1 - ((q0 ^ (q0 << 1)) & 2);
+    const int sxB = 1 - (q1 & 2), syB = 1 - ((q1 ^ (q1 << 1)) & 2);
+    const int dsx = sxB - sxA, dsy = syB - syA;
+    unsigned b8 = (unsigned)(base & 1023) << 3;
+    const char* pb = reinterpret_cast<const char*>(poly);
+#pragma unroll
+    for (int j2 = 0; j2 < 32; ++j2) {
+        // ordering point at the start of every group of 4: the group's address arithmetic starts from a value the
+        // compiler cannot see through, so it is not hoisted (and spilled) ahead of the previous groups
+        if ((j2 & 3) == 0) asm volatile("" : "+r"(b8));
+        const unsigned u = b8 + 256u * j2;                       // byte offset of the rotated pair, bit 13 = crossed
+        const int c = (int)(u >> 13);
+        const uint2 P = *reinterpret_cast<const uint2*>(pb + (u & 8191u));
+        const uint2 O = *reinterpret_cast<const uint2*>(pb + lane * 8 + 256 * j2);
+        const int sw = swA ^ c;
+        const int sx = imad(c, dsx, sxA), sy = imad(c, dsy, syA);
+        const int e = (int)(P.y - P.x);
+        const int px = imad(sw, e, (int)P.x);
+        const int py = (int)(P.x + P.y) - px;
+        const int dx = imad(px, sx, half - (int)O.x);
+        const int dy = imad(py, sy, half - (int)O.y);
+        z[j2].x = __hiloint2double(0x43300000, (dx >> sh) ^ (int)0x80000000) - 4503601774854144.0;
+        z[j2].y = __hiloint2double(0x43300000, (dy >> sh) ^ (int)0x80000000) - 4503601774854144.0;
+        // compiler-only ordering point every 4 elements: the four results must exist here, so the integer halves of
+        // later elements cannot all be computed (and spilled) before the first conversion
+        if ((j2 & 3) == 3) {
+            asm volatile("" : "+d"(z[j2 - 3].x), "+d"(z[j2 - 3].y), "+d"(z[j2 - 2].x), "+d"(z[j2 - 2].y),
+                              "+d"(z[j2 - 1].x), "+d"(z[j2 - 1].y), "+d"(z[j2].x), "+d"(z[j2].y) :: "memory");
+        }
+    }
+}
+template <typename AccT>
+__device__ __forceinline__ void stream_head(int lane, const pair_t<AccT>* poly, int a, int base_log, cplx (&z)[32]) {
+    if constexpr (sizeof(AccT) == 4) stream_head_u32(lane, poly, a, base_log, z);
+    else cmux_head<AccT>(lane, poly, a, base_log, z);
+}
+
 // ---------------------------------------------------------------------------------------
 // Bootstrapping key conversion.  grid = n * 4 polynomials, block = 32.
 // in : bsk [n][p][l=1][q][2048] u64 (standard domain)      out: [n][position][g = 2p+q][lane] cplx
@@ -110,47 +158,65 @@ __global__ void __launch_bounds__(32) bsk_convert_stream_kernel(const uint64_t* 
     for (int s = 0; s < 32; ++s) out[(((size_t)i * 32 + slot_position(s)) * 4 + g) * 32 + lane] = v[s];
 }
 
+// The key ring of this kernel works in half steps: one 32 KB bulk copy brings the GGSW entries of 16 frequencies
+// (one half of the consumption order), NH such stages form the ring.  Producer state lives in every lane of warp 0
+// and advances with warp-uniform control flow (tma_ring.cuh explains why); it never blocks.
+constexpr int kHalfCplx = 16 * 4 * 32;                  // 2048 complex = 32 KiB
+template <int NH>
+struct HalfProducer {
+    int next_h, stage;
+    uint32_t phase;
+    __device__ __forceinline__ void init() { next_h = 0; stage = 0; phase = 1; }
+    __device__ __forceinline__ void poll(int lane, const cplx* bsk_f, cplx* ring, uint64_t* full, uint64_t* empty, int total_halves) {
+        while (next_h < total_halves) {
+            if (!mbar_test(empty + stage, phase)) break;
+            if (lane == 0) {
+                mbar_arrive_expect_tx(full + stage, kHalfCplx * sizeof(cplx));
+                bulk_load(ring + (size_t)stage * kHalfCplx, bsk_f + (size_t)next_h * kHalfCplx, kHalfCplx * sizeof(cplx), full + stage);
+            }
+            __syncwarp();
+            ++next_h;
+            if (++stage == NH) { stage = 0; phase ^= 1; }
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------------------
 // Blind rotation + sample extraction.  One CTA = CTS ciphertexts, two warps each.
-// shared memory: acc [CTS][2][1024] pair_t<AccT> | xbuf [CTS][2][1056] double | ring [NCH][512] cplx |
-//                tables [2080] cplx | full[NCH], empty[NCH] mbarriers | prog[CTS]
-// `mode`: > 0 start offset of ciphertext k by k * mode cycles; < 0 chain mode (ciphertext k starts a step after
-// ciphertext k-1 has finished the head of that step); 0 none.
+// shared memory: acc [CTS][2][1024] pair_t<AccT> | xbuf [CTS][2][1056] double | ring [NH][2048] cplx |
+//                tables [2080] cplx | full[NH], empty[NH] mbarriers
 // ---------------------------------------------------------------------------------------
-template <typename AccT, int CTS, int NCH>
+template <typename AccT, int CTS, int NH>
 __global__ void __launch_bounds__(CTS * 64, 1) pbs_stream_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                                   int n, int base_log, const uint64_t* __restrict__ luts,
                                                                   const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
                                                                   const int32_t* __restrict__ out_idx, int count,
-                                                                  const cplx* __restrict__ tabs_g, int mode, long long* dbg) {
+                                                                  const cplx* __restrict__ tabs_g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pair_t<AccT>* acc_all = reinterpret_cast<pair_t<AccT>*>(smem_raw);
     double* xbuf_all = reinterpret_cast<double*>(smem_raw + (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>));
     cplx* ring = reinterpret_cast<cplx*>(xbuf_all + (size_t)CTS * 2 * kXBufDoubles);
-    cplx* tabs = ring + (size_t)NCH * kChunkCplx;
+    cplx* tabs = ring + (size_t)NH * kHalfCplx;
     uint64_t* full = reinterpret_cast<uint64_t*>(tabs + kTabCplx);
-    uint64_t* empty = full + NCH;
-    volatile int* prog = reinterpret_cast<volatile int*>(empty + NCH);
+    uint64_t* empty = full + NH;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int chain = mode < 0 ? -mode : 0;      // 1: full chain; 2: ct 2,3 trail ct 0 by one head; 4: by head + first pass
-    constexpr bool kWholeStep = NCH >= kChunksPerStep;      // the ring holds a whole step's key
+    static_assert(NH >= 2, "the ring must hold a whole step");
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NCH; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 2 * CTS); }
+        for (int s = 0; s < NH; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 2 * CTS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < CTS) prog[threadIdx.x] = 0;
     for (int t = threadIdx.x; t < kTabCplx; t += CTS * 64) {
         const double2 d = __ldg(reinterpret_cast<const double2*>(tabs_g + t));
         tabs[t].x = d.x; tabs[t].y = d.y;
     }
     __syncthreads();
 
-    const int total_chunks = n * kChunksPerStep;
+    const int total_halves = 2 * n;
     const bool producer = warp == 0;                   // warp-uniform
-    RingProducer<NCH> prod;
+    HalfProducer<NH> prod;
     prod.init();
-#define FSC_POLL() do { if (producer) prod.poll(lane, bsk_f, ring, full, empty, total_chunks); } while (0)
+#define FSC_POLL() do { if (producer) prod.poll(lane, bsk_f, ring, full, empty, total_halves); } while (0)
     FSC_POLL();
 
     const int ctl = warp >> 1, p = warp & 1;
@@ -173,16 +239,9 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_stream_kernel(const cplx* __r
         }
     }
     __syncwarp();
-    if (mode > 0 && ctl > 0) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < (long long)ctl * mode) { }
-        __syncwarp();
-    }
-
     // Fourier-domain product of this warp: X_p <- X_p * G[p][p] + X_{1-p} * G[1-p][p]  (g = 2 row + col)
     const int g_own = 3 * p, g_oth = 2 - p;
     const int row_inv = (32 - lane) & 31;
-    const StridedConsts tab1{tabs + kTabL1 + lane, 32}, tab3{tabs + kTabL3 + lane, 32};
     int a_chunk = 0;
     int stage = 0;
     uint32_t phase = 0;
@@ -190,130 +249,91 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_stream_kernel(const cplx* __r
     for (int i = 0; i < n; ++i) {
         if ((i & 31) == 0) a_chunk = (i + lane < n) ? modswitch(ct[i + lane]) : 0;
         const int a = __shfl_sync(0xffffffffu, a_chunk, i & 31);
-        if (chain == 1 && ctl > 0) { while (prog[ctl - 1] <= i) { } }
-        if (chain >= 2 && ctl >= 2) { while (prog[0] <= i) { } }
-        if (dbg && lane == 0 && blockIdx.x < 4 && (i & 127) == 0) dbg[(blockIdx.x * 16 + warp) * 8 + (i >> 7)] = clock64();
 
-        // ---- quarter 0: head -> pass (uniform table, constant bank) -> transpose store
-        cmux_head<AccT>(lane, acc, a, base_log, X);
-        if (chain && chain < 4 && p == 0 && lane == 0) prog[ctl] = i + 1;
-        pass32(X, UniformConsts<0>());
-        if (chain == 4 && p == 0 && lane == 0) prog[ctl] = i + 1;
-        xp_store(lane, xb, X, 0);
-        __syncwarp();
-
-        // ---- quarter 1: transpose load -> pass (per-lane table) -> Fourier-domain product
-        xp_load(lane, xb, X, 0);
-        __syncwarp();
-        xp_store(lane, xb, X, 1);
-        __syncwarp();
-        xp_load(lane, xb, X, 1);
-        __syncwarp();
-        pass32(X, tab1);
-        if constexpr (kWholeStep) {
-            // Every chunk of this step must have been requested before any warp may sleep on it.  The producer warp
+        auto do_head = [&]() {
+            stream_head<AccT>(lane, acc, a, base_log, X);
+        };
+        auto xp_out = [&](bool after_product) {
+            if (after_product) pair_barrier(1 + ctl);      // deferred from the product: the partner has read this buffer
+            xp_store(lane, xb, X, 0);
+            __syncwarp();
+        };
+        auto xp_in = [&](int row) {
+            xp_load(row, xb, X, 0);
+            __syncwarp();
+            xp_store(lane, xb, X, 1);
+            __syncwarp();
+            xp_load(row, xb, X, 1);
+            __syncwarp();
+        };
+        auto do_mac = [&]() {
+            // Both halves of this step must have been requested before any warp may sleep on them.  The producer warp
             // makes sure of that here, once per step; it cannot deadlock: the stages it waits for are released by
             // the other warps in the product of the previous step, which never waits for warp 0.
             if (producer) {
-                while (prod.next_u < (i + 1) * kChunksPerStep && prod.next_u < total_chunks)
-                    prod.poll(lane, bsk_f, ring, full, empty, total_chunks);
+                while (prod.next_h < 2 * (i + 1) && prod.next_h < total_halves)
+                    prod.poll(lane, bsk_f, ring, full, empty, total_halves);
             }
-            // the ring holds the whole step: wait for the four chunks of a half, then one straight-line block of
-            // 48 shared-memory loads and 128 FMAs that the scheduler is free to interleave
+            // One half = 16 frequencies.  The own-spectrum products need no partner data: they run between the
+            // exchange store and the pair barrier, so the wait for the partner warp hides behind 64 FMAs.
             auto half = [&](auto hc) {
                 constexpr int H = decltype(hc)::value;
 #pragma unroll
                 for (int s = 0; s < 32; ++s)
                     if ((slot_position(s) >> 4) == H) xc[(slot_position(s) & 15) * 32 + lane] = X[s];
-                pair_barrier(1 + ctl);
-                int st[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    st[k] = stage;
-                    mbar_wait(full + stage, phase);
-                    if (++stage == NCH) { stage = 0; phase ^= 1; }
-                }
-                auto chunk = [&](auto kc) {
+                mbar_wait(full + stage, phase);
+                const cplx* g = ring + (size_t)stage * kHalfCplx + lane;
+                auto own = [&](auto kc) {
                     constexpr int K = decltype(kc)::value;
-                    cplx o[4], gw[4], go[4];
-                    const cplx* g = ring + (size_t)st[K] * kChunkCplx + lane;
+                    cplx gw[4];
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) gw[rr] = g[((K * 4 + rr) * 4 + g_own) * 32];
+                    mac_own<H * 16 + K * 4>(X, gw);
+                };
+                own(std::integral_constant<int, 0>{});
+                own(std::integral_constant<int, 1>{});
+                own(std::integral_constant<int, 2>{});
+                own(std::integral_constant<int, 3>{});
+                pair_barrier(1 + ctl);                       // the partner's half is in its exchange buffer
+                auto oth = [&](auto kc) {
+                    constexpr int K = decltype(kc)::value;
+                    cplx o[4], go[4];
 #pragma unroll
                     for (int rr = 0; rr < 4; ++rr) {
                         o[rr] = xother[(K * 4 + rr) * 32 + lane];
-                        gw[rr] = g[(rr * 4 + g_own) * 32];
-                        go[rr] = g[(rr * 4 + g_oth) * 32];
+                        go[rr] = g[((K * 4 + rr) * 4 + g_oth) * 32];
                     }
-                    mac_chunk<H * 16 + K * 4>(X, o, gw, go);
+                    mac_oth<H * 16 + K * 4>(X, o, go);
                 };
-                chunk(std::integral_constant<int, 0>{});
-                chunk(std::integral_constant<int, 1>{});
-                chunk(std::integral_constant<int, 2>{});
-                chunk(std::integral_constant<int, 3>{});
+                oth(std::integral_constant<int, 0>{});
+                oth(std::integral_constant<int, 1>{});
+                oth(std::integral_constant<int, 2>{});
+                oth(std::integral_constant<int, 3>{});
                 __syncwarp();
-                if (lane == 0) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) mbar_arrive(empty + st[k]);
-                }
-                pair_barrier(1 + ctl);
+                if (lane == 0) mbar_arrive(empty + stage);
+                if (++stage == NH) { stage = 0; phase ^= 1; }
+                // the partner must be done with this warp's exchange buffer before it is overwritten: by the second
+                // half's exchange store (H = 0), or by the transpose store after the next pass (H = 1, barrier there)
+                if (H == 0) pair_barrier(1 + ctl);
             };
             half(std::integral_constant<int, 0>{});
             half(std::integral_constant<int, 1>{});
-        } else {
-            auto chunk = [&](auto r0c) {
-                constexpr int R0 = decltype(r0c)::value;
-                cplx o[4], gw[4], go[4];
-#pragma unroll
-                for (int rr = 0; rr < 4; ++rr) o[rr] = xother[((R0 + rr) & 15) * 32 + lane];
-                if (producer) {
-                    // ring shorter than a step: the producer must not sleep on a chunk it has not requested yet
-                    while (!mbar_test(full + stage, phase)) prod.poll(lane, bsk_f, ring, full, empty, total_chunks);
-                } else {
-                    mbar_wait(full + stage, phase);
-                }
-                const cplx* g = ring + (size_t)stage * kChunkCplx + lane;
-#pragma unroll
-                for (int rr = 0; rr < 4; ++rr) { gw[rr] = g[(rr * 4 + g_own) * 32]; go[rr] = g[(rr * 4 + g_oth) * 32]; }
-                mac_chunk<R0>(X, o, gw, go);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty + stage);
-                if (++stage == NCH) { stage = 0; phase ^= 1; }
-                FSC_POLL();
-            };
-#pragma unroll
-            for (int s = 0; s < 32; ++s)
-                if (slot_position(s) < 16) xc[slot_position(s) * 32 + lane] = X[s];
-            pair_barrier(1 + ctl);
-            chunk(std::integral_constant<int, 0>{});
-            chunk(std::integral_constant<int, 4>{});
-            chunk(std::integral_constant<int, 8>{});
-            chunk(std::integral_constant<int, 12>{});
-            pair_barrier(1 + ctl);
-#pragma unroll
-            for (int s = 0; s < 32; ++s)
-                if (slot_position(s) >= 16) xc[(slot_position(s) - 16) * 32 + lane] = X[s];
-            pair_barrier(1 + ctl);
-            chunk(std::integral_constant<int, 16>{});
-            chunk(std::integral_constant<int, 20>{});
-            chunk(std::integral_constant<int, 24>{});
-            chunk(std::integral_constant<int, 28>{});
-            pair_barrier(1 + ctl);
+        };
+        auto do_tail = [&]() {
+            stream_tail<AccT>(lane, acc, tabs + kTabTwist, X);
+            __syncwarp();
+        };
+        // one copy of the pass in the loop body (the body has to fit the instruction cache): q selects the table and
+        // the stages around the pass
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            if (q == 0) do_head();
+            else if (q & 1) xp_in(q == 1 ? lane : row_inv);
+            pass32(X, pass_table(tabs, q, lane));
+            if (!(q & 1)) xp_out(q == 2);
+            else if (q == 1) do_mac();
+            else do_tail();
         }
-
-        // ---- quarter 2: pass (uniform table) -> transpose store
-        pass32(X, UniformConsts<16>());
-        xp_store(lane, xb, X, 0);
-        __syncwarp();
-
-        // ---- quarter 3: transpose load -> pass (per-lane table) -> twist, rounding, accumulation
-        xp_load(row_inv, xb, X, 0);
-        __syncwarp();
-        xp_store(lane, xb, X, 1);
-        __syncwarp();
-        xp_load(row_inv, xb, X, 1);
-        __syncwarp();
-        pass32(X, tab3);
-        stream_tail<AccT>(lane, acc, tabs + kTabTwist, X);
-        __syncwarp();
         FSC_POLL();
     }
 #undef FSC_POLL
@@ -379,34 +399,19 @@ void launch_negacyclic_mul_stream(const uint64_t* a, const int64_t* b, uint64_t*
     negacyclic_mul_stream_kernel<<<count, 32, 0, st>>>(a, b, c, stream_tables<uint64_t>());
 }
 
-template <typename AccT, int CTS, int NCH>
+template <typename AccT, int CTS, int NH>
 static void launch_pbs_stream_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
                                 const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     const size_t smem = (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>) + (size_t)CTS * 2 * kXBufDoubles * sizeof(double) +
-                        (size_t)NCH * kChunkCplx * sizeof(cplx) + (size_t)kTabCplx * sizeof(cplx) + 2 * NCH * sizeof(uint64_t) + 16;
+                        (size_t)NH * kHalfCplx * sizeof(cplx) + (size_t)kTabCplx * sizeof(cplx) + 2 * NH * sizeof(uint64_t);
     static bool configured = false;
     if (!configured) {
-        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_stream_kernel<AccT, CTS, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_stream_kernel<AccT, CTS, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    static int mode = 1 << 30;
-    if (mode == 1 << 30) { const char* e = getenv("FSC_PBS_STAGGER"); mode = e ? atoi(e) : 0; }
     const int grid = (count + CTS - 1) / CTS;
-    static long long* dbg = nullptr;
-    if (!dbg && getenv("FSC_PBS_DEBUG_CLOCKS")) { FSC_CUDA_CHECK(cudaMalloc(&dbg, 4 * 16 * 8 * 8)); FSC_CUDA_CHECK(cudaMemset(dbg, 0, 4 * 16 * 8 * 8)); }
-    pbs_stream_kernel<AccT, CTS, NCH><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts,
-                                                                     lut_idx, out_big, out_idx, count, stream_tables<AccT>(), mode, dbg);
-    if (dbg) {
-        long long h[4 * 16 * 8];
-        FSC_CUDA_CHECK(cudaStreamSynchronize(st));
-        FSC_CUDA_CHECK(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
-        for (int b = 0; b < 2; ++b)
-            for (int k = 0; k < 7; ++k) {
-                fprintf(stderr, "block %d step %4d:", b, k * 128);
-                for (int w = 0; w < CTS * 2; ++w) fprintf(stderr, " %8lld", h[(b * 16 + w) * 8 + k] - h[(b * 16) * 8 + k]);
-                fprintf(stderr, "   (step time %lld)\n", k ? (h[(b * 16) * 8 + k] - h[(b * 16) * 8 + k - 1]) / 128 : 0);
-            }
-    }
+    pbs_stream_kernel<AccT, CTS, NH><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts,
+                                                                          lut_idx, out_big, out_idx, count, stream_tables<AccT>());
 }
 
 // Configuration by batch width: wide levels pack 4 (u32 accumulator) or 3 (u64) ciphertexts per CTA so that one key
@@ -415,16 +420,17 @@ static void launch_pbs_stream_t(const void* bsk_f, const uint64_t* in_small, int
 void launch_pbs_stream(int acc_bits, const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
                        const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, int sm_count, cudaStream_t st) {
     if (count <= 0) return;
-#define FSC_STREAM(ACC, CTS, NCH) \
-    launch_pbs_stream_t<ACC, CTS, NCH>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st)
+#define FSC_STREAM(ACC, CTS, NH) \
+    launch_pbs_stream_t<ACC, CTS, NH>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st)
     if (acc_bits == 32) {
-        if (count <= sm_count) FSC_STREAM(uint32_t, 1, 10);
-        else if (count <= 2 * sm_count) FSC_STREAM(uint32_t, 2, 10);
-        else FSC_STREAM(uint32_t, 4, 8);
+        if (count <= sm_count) FSC_STREAM(uint32_t, 1, 3);
+        else if (count <= 2 * sm_count) FSC_STREAM(uint32_t, 2, 3);
+        else FSC_STREAM(uint32_t, 4, 2);
     } else {
-        if (count <= sm_count) FSC_STREAM(uint64_t, 1, 10);
-        else if (count <= 2 * sm_count) FSC_STREAM(uint64_t, 2, 10);
-        else FSC_STREAM(uint64_t, 3, 5);
+        // 64-bit accumulator: two ciphertexts per CTA is what fits beside a whole-step ring (the product default for
+        // 64-bit accumulators is the ring kernel of pbs_kernel.cu, three per CTA)
+        if (count <= sm_count) FSC_STREAM(uint64_t, 1, 3);
+        else FSC_STREAM(uint64_t, 2, 2);
     }
 #undef FSC_STREAM
 }

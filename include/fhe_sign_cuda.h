@@ -205,6 +205,9 @@ fsc_status fsc_timer_start(fsc_ctx *ctx);
 fsc_status fsc_timer_stop(fsc_ctx *ctx, float *elapsed_ms);     /* synchronises */
 /* number of kernels this context has launched so far                                             */
 fsc_status fsc_launch_count(const fsc_ctx *ctx, uint64_t *out);
+/* Name of the blind-rotation kernel this context uses for wide batches ("pbs_stream_kernel",
+ * "pbs_ring_kernel" or "pbs_pair_kernel"; fixed at fsc_keys_upload).  Static string. */
+const char *fsc_pbs_kernel_name(const fsc_ctx *ctx);
 /* Measures the device's sustained FP64 FMA rate (TFLOP/s, 2 flops per FMA) with a register-resident
  * FMA-chain kernel: the denominator of the blind rotation's compute roofline.                   */
 fsc_status fsc_measure_fp64_peak(fsc_ctx *ctx, double *tflops);

@@ -77,6 +77,37 @@ def test_pbs_all_messages_all_luts(gpu_ctx, oracle_keys, rng, preset, acc_bits):
     din.free(); dout.free(); luts.free()
 
 
+@pytest.mark.parametrize("acc_bits", [32, 64])
+@pytest.mark.parametrize("variant", ["stream", "ring", "pair"])
+def test_pbs_kernel_variants_all_widths(oracle_keys, orc, rng, variant, acc_bits, monkeypatch):
+    """Every blind-rotation kernel (FSC_PBS_VARIANT) at batch widths that select each of its configurations
+    (1, 2 and 3-4 ciphertexts per CTA, ragged last CTA): decrypted values equal the table, noise inside the budget.
+    The Fourier key layout follows the variant, so this also checks both key conversions."""
+    import fhe_sign_b200 as fsb
+    from fhe_sign_b200.capi import LWE_BIG
+    monkeypatch.setenv("FSC_PBS_VARIANT", variant)
+    K = oracle_keys("toy")
+    ctx = fsb.Context(fsb.Params.preset("toy", acc_bits=acc_bits))
+    ctx.upload_keys(K.bsk, K.ksk)
+    table = rng.integers(0, 16, 16).astype(np.uint64)
+    luts = ctx.luts_from_tables(table)
+    sms = 148
+    for count in (3, sms + 5, 2 * sms + 7):
+        m = rng.integers(0, 16, count).astype(np.uint64)
+        din, dout = ctx.lwe(LWE_BIG, count).upload(K.encrypt_msgs(m)), ctx.lwe(LWE_BIG, count)
+        ctx.ks_pbs(din, luts, None, dout)
+        out = dout.download()
+        assert (K.decrypt_msgs(out) == table[m]).all(), (variant, acc_bits, count)
+        assert np.abs(_noise(K, out, table[m])).max() < 2.0**-7
+        din.free(); dout.free()
+    a = rng.integers(0, 2**64, (2, 2048), dtype=np.uint64)
+    b = rng.integers(-2**22, 2**22, (2, 2048), dtype=np.int64)
+    c = ctx.debug_negacyclic_mul(a, b)
+    for i in range(2):
+        assert np.abs((c[i] - orc.negacyclic_mul_exact(a[i], b[i])).astype(np.int64)).max() < 2**43
+    ctx.close()
+
+
 def test_lut_polynomials_match_oracle(gpu_ctx, oracle_keys, rng):
     """fsc_luts_from_tables builds the same accumulator the oracle does: PBS through uploaded oracle
     polynomials and through library-built ones decrypt identically."""
