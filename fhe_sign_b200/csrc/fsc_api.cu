@@ -63,6 +63,7 @@ Engine::~Engine() {
     cudaSetDevice(dev);
     cudaStreamSynchronize(stream);
     if (bsk_f) cudaFree(bsk_f);
+    if (bsk_s) cudaFree(bsk_s);
     if (ksk) cudaFree(ksk);
     if (ksk_limbs) cudaFree(ksk_limbs);
     if (ks_digits) cudaFree(ks_digits);
@@ -85,6 +86,7 @@ void Engine::upload_keys(const uint64_t* bsk_std, size_t bsk_words, const uint64
     FSC_REQUIRE(bsk_words == want_bsk, "bootstrapping key size does not match the parameter set");
     FSC_REQUIRE(ksk_words == want_ksk, "keyswitching key size does not match the parameter set");
     if (bsk_f) { cudaFree(bsk_f); bsk_f = nullptr; }
+    if (bsk_s) { cudaFree(bsk_s); bsk_s = nullptr; }
     if (ksk) { cudaFree(ksk); ksk = nullptr; }
     if (ksk_limbs) { cudaFree(ksk_limbs); ksk_limbs = nullptr; }
     uint64_t* tmp = nullptr;
@@ -99,6 +101,12 @@ void Engine::upload_keys(const uint64_t* bsk_std, size_t bsk_words, const uint64
     if (pbs_variant == 2) launch_bsk_convert_stream(tmp, bsk_f, (int)n, stream);      // the stream kernel's key order
     else launch_bsk_convert(tmp, bsk_f, (int)n, stream);
     ++launches;
+    if (pbs_variant == 3) {      // both kernels: second copy of the Fourier key in the stream kernel's order
+        e = cudaMalloc(&bsk_s, n * 32 * 4 * 32 * 16);
+        if (e != cudaSuccess) { cudaFree(tmp); FSC_CUDA_CHECK(e); }
+        launch_bsk_convert_stream(tmp, bsk_s, (int)n, stream);
+        ++launches;
+    }
     FSC_CUDA_CHECK(cudaGetLastError());
     {
         const size_t K = (size_t)N * p.ks_level;
@@ -176,7 +184,12 @@ void Engine::pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut
                  const int32_t* out_idx_dev) {
     use();
     if (!bsk_f) throw Error(FSC_ERR_NO_KEYS, "server keys not uploaded");
-    if (pbs_variant == 2)
+    // variant 3: narrow levels (at most two ciphertexts per SM: the latency-bound case) on the stream kernel, wide
+    // batches on the ring kernel
+    if (pbs_variant == 3 && (int)count <= 2 * sm_count)
+        launch_pbs_stream((int)p.acc_bits, bsk_s, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, out_big,
+                          out_idx_dev, (int)count, sm_count, stream);
+    else if (pbs_variant == 2)
         launch_pbs_stream((int)p.acc_bits, bsk_f, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, out_big,
                           out_idx_dev, (int)count, sm_count, stream);
     else
@@ -474,7 +487,7 @@ fsc_status fsc_launch_count(const fsc_ctx* ctx, uint64_t* out) {
 const char* fsc_pbs_kernel_name(const fsc_ctx* ctx) {
     if (!ctx) return "";
     const int v = ctx->eng->bsk_f ? ctx->eng->pbs_variant : fsc::pbs_variant_for((int)ctx->eng->p.acc_bits);
-    return v == 2 ? "pbs_stream_kernel" : v == 1 ? "pbs_ring_kernel" : "pbs_pair_kernel";
+    return v == 2 ? "pbs_stream_kernel" : v == 0 ? "pbs_pair_kernel" : "pbs_ring_kernel";
 }
 
 fsc_status fsc_measure_fp64_peak(fsc_ctx* ctx, double* tflops) {

@@ -41,7 +41,8 @@ void launch_pbs_stream(int acc_bits, const void* bsk_fourier, const uint64_t* in
                        const uint64_t* luts, const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count,
                        int sm_count, cudaStream_t st);
 void launch_negacyclic_mul_stream(const uint64_t* a, const int64_t* b, uint64_t* c, int count, cudaStream_t st);
-// 0: pair, 1: ring, 2: stream (FSC_PBS_VARIANT, else by accumulator width); fixed per context at key upload
+// 0: pair, 1: ring, 2: stream, 3: ring (wide) + stream (narrow) (FSC_PBS_VARIANT, else by accumulator width);
+// fixed per context at key upload
 int pbs_variant_for(int acc_bits);
 
 double launch_fp64_peak(double* sink, int sm_count, int iters, cudaStream_t st);

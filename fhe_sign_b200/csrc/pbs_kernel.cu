@@ -453,15 +453,17 @@ static void launch_pbs_ring_t(const void* bsk_f, const uint64_t* in_small, int n
 }
 
 // Which blind-rotation kernel a context uses (fixed at key upload, because the Fourier key layout differs):
-// FSC_PBS_VARIANT = "pair" (first version, one ciphertext per CTA) | "ring" | "stream"; default: stream for the 32-bit
-// accumulator, ring for the 64-bit accumulator (three ciphertexts per CTA do not fit beside the stream kernel's
-// whole-step key ring).
+// FSC_PBS_VARIANT = "pair" (first version, one ciphertext per CTA) | "ring" | "stream" | "auto".  Default:
+// 32-bit accumulator: auto (3) = ring kernel for wide batches (70-72 k PBS/s against 68-70 k) and stream kernel for
+// levels of at most two ciphertexts per SM (5.2-5.6 ms per level against 6.9-7.0 ms), one Fourier key copy each;
+// 64-bit accumulator: ring (three ciphertexts per CTA do not fit beside the stream kernel's whole-step key ring).
 int pbs_variant_for(int acc_bits) {
     const char* e = getenv("FSC_PBS_VARIANT");
     if (e && e[0] == 'p') return 0;
     if (e && e[0] == 'r') return 1;
     if (e && e[0] == 's') return 2;
-    return acc_bits == 32 ? 2 : 1;
+    if (e && e[0] == 'a') return 3;
+    return acc_bits == 32 ? 3 : 1;
 }
 
 // Ring kernel configuration by batch width: wide levels pack 4 (u32 accumulator) or 3 (u64) ciphertexts per CTA
@@ -473,7 +475,7 @@ void launch_pbs(int variant, int acc_bits, const void* bsk_f, const uint64_t* in
     if (count <= 0) return;
 #define FSC_RING(ACC, CTS, NCH) \
     launch_pbs_ring_t<ACC, CTS, NCH, true, 0>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st)
-    if (variant == 0) {
+    if (variant == 0) {      // variants 1 and 3 use the ring kernel here
         if (acc_bits == 32) launch_pbs_pair_t<uint32_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
         else launch_pbs_pair_t<uint64_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
     } else if (acc_bits == 32) {

@@ -1,11 +1,6 @@
 mkdir -p gpurun_out
-L=gpurun_out/e43.log
-: > $L
-for o in "2000,1200" "0,0" "4500,2000" "2000,400"; do
-echo -n "offsets $o: " >> $L
-FSC_PBS_VARIANT=stream FSC_PBS_OFFSETS=$o timeout 100 python tools/prof_pbs.py 4096 1 2>&1 | grep -E "pbs" >> $L
-done
-for c in 100 148 296; do
-FSC_PBS_VARIANT=stream timeout 100 python tools/prof_pbs.py $c 2 2>&1 | grep pbs | tail -1 >> $L
-done
-cat $L
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/e45_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/e45_pytest.log
+tail -4 gpurun_out/e45_pytest.log
+timeout 600 python bench.py > gpurun_out/e45_bench32.json 2> gpurun_out/e45_bench32.err; python -c "
+import json; d=json.load(open('gpurun_out/e45_bench32.json')); print(d['value'], d['roofline']['frac'], d['roofline']['kernel'], d['e2e']['value'])"
+timeout 900 python tools/op_bench.py > gpurun_out/e45_ops.jsonl 2> gpurun_out/e45_ops.err; cat gpurun_out/e45_ops.jsonl | cut -c1-200
