@@ -95,6 +95,35 @@ FSC_HD void pass32(cplx (&v)[32], const SP& sp) {
     }
 }
 
+// Gentleman-Sande inverse of pass32 (exact reverse up to a factor 32) reading the same table: entry 0 is (re, im),
+// entries >= 1 are (cos, tan) and are turned back into (re, im) with one multiply.  Used by the ring kernel, whose
+// inverse keeps the merged-twist Gentleman-Sande form.
+template <class SP>
+FSC_HD void pass32_inv_gs(cplx (&v)[32], const SP& sp) {
+#pragma unroll
+    for (int L = 5; L >= 1; --L) {
+        const int half = 16 >> (L - 1);
+#pragma unroll
+        for (int m = 0; m < (1 << (L - 1)); ++m) {
+            const int base = m * 2 * half;
+            const int ci = (L == 1) ? 0 : ((1 << (L - 2)) + (m >> 1));
+            const bool odd = (L > 1) && (m & 1);
+            cplx s = sp.get(ci);
+            if (ci > 0) s.y = s.x * s.y;
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+                const cplx u = v[base + j], w2 = v[base + half + j];
+                const double dx = u.x - w2.x, dy = u.y - w2.y;
+                v[base + j].x = u.x + w2.x; v[base + j].y = u.y + w2.y;
+                const double ex = s.x * dx + s.y * dy;       // conj(s) * d
+                const double ey = s.x * dy - s.y * dx;
+                if (!odd) { v[base + half + j].x = ex; v[base + half + j].y = ey; }
+                else      { v[base + half + j].x = ey; v[base + half + j].y = -ex; }   // -i * conj(s) * d
+            }
+        }
+    }
+}
+
 struct StridedConsts {      // table entry ci at base[ci * stride] (stride 1: uniform table, 32: per-lane table)
     const cplx* base;
     int stride;

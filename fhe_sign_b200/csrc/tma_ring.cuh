@@ -81,4 +81,27 @@ struct RingProducer {
     }
 };
 
+// Half-step ring: one 32 KB bulk copy brings the GGSW entries of 16 frequencies
+// (one half of the consumption order), NH such stages form the ring.  Producer state lives in every lane of warp 0
+// and advances with warp-uniform control flow (tma_ring.cuh explains why); it never blocks.
+constexpr int kHalfCplx = 16 * 4 * 32;                  // 2048 complex = 32 KiB
+template <int NH>
+struct HalfProducer {
+    int next_h, stage;
+    uint32_t phase;
+    __device__ __forceinline__ void init() { next_h = 0; stage = 0; phase = 1; }
+    __device__ __forceinline__ void poll(int lane, const cplx* bsk_f, cplx* ring, uint64_t* full, uint64_t* empty, int total_halves) {
+        while (next_h < total_halves) {
+            if (!mbar_test(empty + stage, phase)) break;
+            if (lane == 0) {
+                mbar_arrive_expect_tx(full + stage, kHalfCplx * sizeof(cplx));
+                bulk_load(ring + (size_t)stage * kHalfCplx, bsk_f + (size_t)next_h * kHalfCplx, kHalfCplx * sizeof(cplx), full + stage);
+            }
+            __syncwarp();
+            ++next_h;
+            if (++stage == NH) { stage = 0; phase ^= 1; }
+        }
+    }
+};
+
 }  // namespace fsc
