@@ -30,7 +30,7 @@ WORKLOAD = "batched PBS microbench: %d LWE blocks, PARAM_MESSAGE_2_CARRY_2 (%s),
 
 
 # DRAM bytes (read + write) of one 4096-block launch, from the ncu --set full captures summarised in profiles/
-NCU_TRAFFIC = {"pbs_ring_kernel": 252.07e6, "pbs_stream_kernel": None}
+NCU_TRAFFIC = {"pbs_ring_kernel": 216.18e6, "pbs_stream_kernel": 263.39e6}      # profiles/r01b_ncu_key_metrics.json
 
 
 def flops_per_pbs(n, N=2048, k=1, l=1):
@@ -159,6 +159,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     # synthetic key material of the right shape (PBS/keyswitch cost is data independent); the oracle is
@@ -263,7 +264,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only (torchrun pins OMP_NUM_THREADS=1)
             from oracle import orc
             okeys = orc.Keys(orc.preset(PRESET), 1)
             threads = orc.max_threads()

@@ -1,14 +1,6 @@
 mkdir -p gpurun_out
-L=gpurun_out/e47.log
-: > $L
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/e47_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/e47_pytest.log
-tail -3 gpurun_out/e47_pytest.log >> $L
-for v in ring stream; do for c in 148 296 4096; do
-echo -n "$v acc32 $c: " >> $L
-FSC_PBS_VARIANT=$v timeout 100 python tools/prof_pbs.py $c 2 2>&1 | grep pbs | tail -1 >> $L
-done; done
-for c in 148 296 4096; do
-echo -n "ring acc64 $c: " >> $L
-FSC_BENCH_ACC_BITS=64 timeout 100 python tools/prof_pbs.py $c 2 2>&1 | grep pbs | tail -1 >> $L
-done
-cat $L
+timeout 900 python tools/op_bench.py > gpurun_out/r01b_ops_n1.jsonl 2> gpurun_out/r01b_ops_n1.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_ops.py > gpurun_out/r01b_ops_256bit_n2.jsonl 2> gpurun_out/r01b_ops_n2.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r01b_bench_n2.json 2> gpurun_out/r01b_bench_n2.err
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r01b_bench_ref.json 2> gpurun_out/r01b_bench_ref.err
+cut -c1-160 gpurun_out/r01b_ops_n1.jsonl; cut -c1-200 gpurun_out/r01b_ops_256bit_n2.jsonl; tail -3 gpurun_out/r01b_ops_n2.err; head -c 300 gpurun_out/r01b_bench_n2.json; echo; head -c 400 gpurun_out/r01b_bench_ref.json
