@@ -77,31 +77,11 @@ FSC_HD constexpr int node_exponent(int ci, int g) {
     return (32 >> node_level(ci)) * g + 64 * brev5(2 * (node_level(ci) == 1 ? 0 : ci - (1 << (node_level(ci) - 2))));
 }
 
-// Tangent ("FMA") form of a unit constant s = exp(2 pi i e / 4096): form 1 keeps (w, t) = (cos, sin/cos) when the
-// cosine dominates, form 2 keeps (sin, cos/sin) otherwise, so that |t| <= 1 and  a +- s*b  costs 6 FMAs:
-//   form 1:  s*b = w * ((bx - t by) + i (by + t bx))        form 2:  s*b = w * ((t bx - by) + i (t by + bx))
-FSC_HD constexpr int tan_form(int e) { return ((e & 2047) <= 512 || (e & 2047) >= 1536) ? 1 : 2; }
-// form of stored constant ci of a pass whose lanes are centred on g_center; levels below min_level stay (re, im)
-FSC_HD constexpr int node_form(int ci, int g_center, int min_level) {
-    return node_level(ci) < min_level ? 0 : tan_form(node_exponent(ci, g_center));
-}
-
 FSC_HD void lane_consts(int g, cplx (&s)[16]) {
 #pragma unroll
     for (int ci = 0; ci < 16; ++ci) s[ci] = twiddle4096(node_exponent(ci, g));
 }
-FSC_HD cplx tan_const(int e, int form) {
-    const cplx s = twiddle4096(e);
-    cplx r;
-    if (form == 1) { r.x = s.x; r.y = s.y / s.x; } else if (form == 2) { r.x = s.y; r.y = s.x / s.y; } else r = s;
-    return r;
-}
-FSC_HD void lane_consts_tan(int g, int g_center, int min_level, cplx (&s)[16]) {
-#pragma unroll
-    for (int ci = 0; ci < 16; ++ci) s[ci] = tan_const(node_exponent(ci, g), node_form(ci, g_center, min_level));
-}
-constexpr int kP1Center = 32, kP1MinLevel = 1;      // pass 1: uniform constants, all levels in tangent form
-constexpr int kP2Center = 63, kP2MinLevel = 3;      // pass 2: per-lane constants, levels 3..5 stay inside one octant
+constexpr int kP1G = 32;      // root parameter of pass 1 (uniform): x^32 = zeta^(32 * 32) = i
 
 // ---- 32-point passes ------------------------------------------------------------------
 // SP::get(ci) returns stored constant ci.
@@ -133,106 +113,6 @@ FSC_HD void dft32_fwd(cplx (&v)[32], const SP& sp) {
     }
 }
 
-// forward pass with constants stored in tangent form where node_form says so (6 FMAs per butterfly)
-template <int G_CENTER, int MIN_LEVEL, class SP>
-FSC_HD void dft32_fwd_tan(cplx (&v)[32], const SP& sp) {
-#pragma unroll
-    for (int L = 1; L <= 5; ++L) {
-        const int half = 16 >> (L - 1);
-#pragma unroll
-        for (int m = 0; m < (1 << (L - 1)); ++m) {
-            const int base = m * 2 * half;
-            const int ci = (L == 1) ? 0 : ((1 << (L - 2)) + (m >> 1));
-            const bool odd = (L > 1) && (m & 1);
-            const int form = node_form(ci, G_CENTER, MIN_LEVEL);
-            const cplx s = sp.get(ci);
-#pragma unroll
-            for (int j = 0; j < half; ++j) {
-                const cplx lo = v[base + j], hi = v[base + half + j];
-                double tx, ty;
-                if (form == 0) { tx = s.x * hi.x - s.y * hi.y; ty = s.x * hi.y + s.y * hi.x; }
-                else if (form == 1) { tx = fma(-s.y, hi.y, hi.x); ty = fma(s.y, hi.x, hi.y); }
-                else { tx = fma(s.y, hi.x, -hi.y); ty = fma(s.y, hi.y, hi.x); }
-                const double w = form == 0 ? 1.0 : s.x;
-                if (!odd) {
-                    v[base + j].x = fma(w, tx, lo.x);         v[base + j].y = fma(w, ty, lo.y);
-                    v[base + half + j].x = fma(-w, tx, lo.x); v[base + half + j].y = fma(-w, ty, lo.y);
-                } else {   // constant is i*s
-                    v[base + j].x = fma(-w, ty, lo.x);        v[base + j].y = fma(w, tx, lo.y);
-                    v[base + half + j].x = fma(w, ty, lo.x);  v[base + half + j].y = fma(-w, tx, lo.y);
-                }
-            }
-        }
-    }
-}
-
-// Inverse of pass 1 as a plain inverse DFT (decimation in time: bit-reversed in, natural out, twiddle before
-// add, mostly trivial twiddles) followed by the fused untwist * scale:
-//   out[j2] = tw[j2] * sum_k2 v[brev5(k2)] omega_32^(-j2 k2),   tw[j2] = scale * exp(-2 pi i j2 / 128).
-// cp.get(16 + j): omega_32^(-j) in tangent form, j < 16;  cp.get(tw_base + j2): tw[j2] as (re, im).
-template <int ST, class SP>
-FSC_HD void idft32_dit_stage(cplx (&v)[32], const SP& cp) {
-    constexpr int half = 1 << (ST - 1), m = 2 * half, nblk = 32 / m;
-#pragma unroll
-    for (int blk = 0; blk < nblk; ++blk) {
-#pragma unroll
-        for (int j = 0; j < half; ++j) {
-            const int b = blk * m;
-            const int widx = j * (32 / m);                     // omega_m^-j = omega_32^-(j 32/m)
-            const cplx u = v[b + j], h = v[b + j + half];
-            if (widx == 0) {
-                v[b + j].x = u.x + h.x; v[b + j].y = u.y + h.y;
-                v[b + j + half].x = u.x - h.x; v[b + j + half].y = u.y - h.y;
-            } else if (widx == 8) {                            // w = -i:  w*h = (h.y, -h.x)
-                v[b + j].x = u.x + h.y; v[b + j].y = u.y - h.x;
-                v[b + j + half].x = u.x - h.y; v[b + j + half].y = u.y + h.x;
-            } else {
-                const int form = tan_form(4096 - 128 * widx);
-                const cplx s = cp.get(16 + widx);
-                double tx, ty;
-                if (form == 1) { tx = fma(-s.y, h.y, h.x); ty = fma(s.y, h.x, h.y); }
-                else { tx = fma(s.y, h.x, -h.y); ty = fma(s.y, h.y, h.x); }
-                v[b + j].x = fma(s.x, tx, u.x);         v[b + j].y = fma(s.x, ty, u.y);
-                v[b + j + half].x = fma(-s.x, tx, u.x); v[b + j + half].y = fma(-s.x, ty, u.y);
-            }
-        }
-    }
-}
-template <class SP>
-FSC_HD void idft32_dit_twist(cplx (&v)[32], const SP& cp, int tw_base) {
-    idft32_dit_stage<1>(v, cp);
-    idft32_dit_stage<2>(v, cp);
-    idft32_dit_stage<3>(v, cp);
-    idft32_dit_stage<4>(v, cp);
-    idft32_dit_stage<5>(v, cp);
-#pragma unroll
-    for (int j2 = 0; j2 < 32; ++j2) {
-        const cplx t = cp.get(tw_base + j2), x = v[j2];
-        v[j2].x = x.x * t.x - x.y * t.y;
-        v[j2].y = x.x * t.y + x.y * t.x;
-    }
-}
-
-// table behind the uniform-constant provider of the kernels: 16 pass-1 forward constants (tangent form),
-// 16 omega_32^-j (tangent form), 32 untwist constants scaled for the 64-bit accumulator, 32 for the 32-bit one
-constexpr int kUniTw64 = 32, kUniTw32 = 64, kUniPlainP1 = 96, kUniSize = 112;
-inline void fill_uniform_table(cplx* t) {
-    cplx p1[16];
-    lane_consts_tan(kP1Center, kP1Center, kP1MinLevel, p1);
-    for (int i = 0; i < 16; ++i) t[i] = p1[i];
-    for (int j = 0; j < 16; ++j) t[16 + j] = tan_const(4096 - 128 * j, j == 0 ? 0 : tan_form(4096 - 128 * j));
-    {
-        cplx pl[16];
-        lane_consts(kP1Center, pl);
-        for (int i = 0; i < 16; ++i) t[kUniPlainP1 + i] = pl[i];
-    }
-    for (int j = 0; j < 32; ++j) {
-        const cplx e = twiddle4096(4096 - 32 * j);
-        t[kUniTw64 + j].x = e.x * (1.0 / 1024.0);          t[kUniTw64 + j].y = e.y * (1.0 / 1024.0);
-        t[kUniTw32 + j].x = e.x * (1.0 / 4398046511104.0); t[kUniTw32 + j].y = e.y * (1.0 / 4398046511104.0);
-    }
-}
-
 // exact reverse of dft32_fwd up to a factor 32
 template <class SP>
 FSC_HD void dft32_inv(cplx (&v)[32], const SP& sp) {
@@ -254,34 +134,6 @@ FSC_HD void dft32_inv(cplx (&v)[32], const SP& sp) {
                 const double ey = s.x * dy - s.y * dx;
                 if (!odd) { v[base + half + j].x = ex; v[base + half + j].y = ey; }
                 else      { v[base + half + j].x = ey; v[base + half + j].y = -ex; }   // -i * conj(s) * d
-            }
-        }
-    }
-}
-
-// inverse pass whose constants come from a tangent-form table (plain (re, im) rebuilt with one multiply)
-template <int G_CENTER, int MIN_LEVEL, class SP>
-FSC_HD void dft32_inv_tan(cplx (&v)[32], const SP& sp) {
-#pragma unroll
-    for (int L = 5; L >= 1; --L) {
-        const int half = 16 >> (L - 1);
-#pragma unroll
-        for (int m = 0; m < (1 << (L - 1)); ++m) {
-            const int base = m * 2 * half;
-            const int ci = (L == 1) ? 0 : ((1 << (L - 2)) + (m >> 1));
-            const bool odd = (L > 1) && (m & 1);
-            const int form = node_form(ci, G_CENTER, MIN_LEVEL);
-            cplx s = sp.get(ci);
-            if (form == 1) { s.y = s.x * s.y; } else if (form == 2) { const double w = s.x; s.x = w * s.y; s.y = w; }
-#pragma unroll
-            for (int j = 0; j < half; ++j) {
-                const cplx u = v[base + j], w2 = v[base + half + j];
-                const double dx = u.x - w2.x, dy = u.y - w2.y;
-                v[base + j].x = u.x + w2.x; v[base + j].y = u.y + w2.y;
-                const double ex = s.x * dx + s.y * dy;
-                const double ey = s.x * dy - s.y * dx;
-                if (!odd) { v[base + half + j].x = ex; v[base + half + j].y = ey; }
-                else      { v[base + half + j].x = ey; v[base + half + j].y = -ex; }
             }
         }
     }
@@ -424,22 +276,6 @@ template <> FSC_HD uint32_t to_acc<uint32_t>(double v) { return to_torus32(v * (
 template <typename AccT> FSC_HD AccT to_acc_scaled(double v);
 template <> FSC_HD uint64_t to_acc_scaled<uint64_t>(double v) { return to_torus64(v); }
 template <> FSC_HD uint32_t to_acc_scaled<uint32_t>(double v) { return to_torus32(v); }
-template <typename AccT>
-FSC_HD void cmux_tail_scaled(int lane, pair_t<AccT>* poly, const cplx (&y)[32]) {
-#pragma unroll
-    for (int j2 = 0; j2 < 32; ++j2) {
-        const int idx = lane + 32 * j2;
-        pair_t<AccT> O = poly[idx];
-        O.x = (AccT)(O.x + to_acc_scaled<AccT>(y[j2].x));
-        O.y = (AccT)(O.y + to_acc_scaled<AccT>(y[j2].y));
-        poly[idx] = O;
-        FSC_SCHED_FENCE(j2, FSC_FENCE_EVERY);
-    }
-}
-template <typename AccT> struct uni_tw { };
-template <> struct uni_tw<uint64_t> { static constexpr int base = kUniTw64; };
-template <> struct uni_tw<uint32_t> { static constexpr int base = kUniTw32; };
-
 // tail: acc[idx] += round(y / 1024)
 template <typename AccT>
 FSC_HD void cmux_tail(int lane, pair_t<AccT>* poly, const cplx (&y)[32]) {

@@ -19,62 +19,48 @@
 
 namespace fsc {
 
-__constant__ cplx c_uni[kUniSize];     // uniform constants (pbs_core.cuh fill_uniform_table)
+__constant__ cplx c_p1[16];            // forward pass 1 / inverse pass 1 node constants (re, im), g = 32 (pbs_core.cuh lane_consts)
 __constant__ cplx c_wt0[16];           // forward pass 1 in pass32 form (pbs_core2.cuh pass_const, g = 32)
+struct S1PlainDev {
+    __device__ __forceinline__ cplx get(int ci) const { return c_p1[ci]; }
+};
 struct WT0Dev {
     __device__ __forceinline__ cplx get(int ci) const { return c_wt0[ci]; }
 };
 
-struct S1Dev {
-    __device__ __forceinline__ cplx get(int ci) const { return c_uni[ci]; }
-};
-
 void pbs_init_constants() {
-    cplx h[kUniSize];
-    fill_uniform_table(h);
-    FSC_CUDA_CHECK(cudaMemcpyToSymbol(c_uni, h, sizeof(h)));
-    cplx w[16];
-    for (int ci = 0; ci < 16; ++ci) w[ci] = pass_const(ci, 32);
+    cplx h[16], w[16];
+    lane_consts(kP1G, h);
+    for (int ci = 0; ci < 16; ++ci) w[ci] = pass_const(ci, kP1G);
+    FSC_CUDA_CHECK(cudaMemcpyToSymbol(c_p1, h, sizeof(h)));
     FSC_CUDA_CHECK(cudaMemcpyToSymbol(c_wt0, w, sizeof(w)));
 }
 
-// forward negacyclic FFT of the 32 x 32 complex points held by the warp (v[j2] at lane j1)
-struct S1PlainDev {
-    __device__ __forceinline__ cplx get(int ci) const { return c_uni[kUniPlainP1 + ci]; }
-};
-// FFT formulation switches (bit 0: tangent-form forward pass 1, bit 1: tangent-form forward pass 2 levels 3..5,
-// bit 2: inverse pass 1 as DIT + fused untwist/scale).  FV selects what the blind-rotation kernels use.
-template <int FV> struct fft_opts {
-    static constexpr bool f1 = FV & 1, f2 = (FV >> 1) & 1, i1 = (FV >> 2) & 1;
-    static constexpr int p2_min_level = f2 ? kP2MinLevel : 6;      // 6: per-lane table stays (re, im)
-};
-// c2: the 16 per-lane pass-2 constants (lane_consts_tan with kP2Center / fft_opts<FV>::p2_min_level)
-template <int FV, class C2>
+// Negacyclic FFT of the 32 x 32 complex points held by the warp (v[j2] at lane j1), plain (re, im) constants:
+// Cooley-Tukey forward, Gentleman-Sande inverse (exact reverse up to the factor 1024 that the tail removes).
+// c2: the 16 per-lane pass-2 constants (lane_consts(4 lane + 1)).  Full-size (16 KiB) transpose buffer ...
+template <class C2>
 __device__ __forceinline__ void warp_fft_fwd_c(int lane, cplx* xbuf, const C2& c2, cplx (&v)[32]) {
-    if (fft_opts<FV>::f1) dft32_fwd_tan<kP1Center, kP1MinLevel>(v, S1Dev());
-    else dft32_fwd(v, S1PlainDev());
+    dft32_fwd(v, S1PlainDev());
     xpose_store_fwd(lane, xbuf, v);
     __syncwarp();
     xpose_load_fwd(lane, xbuf, v);
     __syncwarp();
-    dft32_fwd_tan<kP2Center, fft_opts<FV>::p2_min_level>(v, c2);
+    dft32_fwd(v, c2);
 }
-// with fft_opts<FV>::i1 the result is already scaled (TW_BASE table); otherwise the tail scales
-template <int FV, int TW_BASE, class C2>
+template <class C2>
 __device__ __forceinline__ void warp_fft_inv_c(int lane, cplx* xbuf, const C2& c2, cplx (&v)[32]) {
-    dft32_inv_tan<kP2Center, fft_opts<FV>::p2_min_level>(v, c2);
+    dft32_inv(v, c2);
     xpose_store_inv(lane, xbuf, v);
     __syncwarp();
     xpose_load_inv(lane, xbuf, v);
     __syncwarp();
-    if (fft_opts<FV>::i1) idft32_dit_twist(v, S1Dev(), TW_BASE);
-    else dft32_inv(v, S1PlainDev());
+    dft32_inv(v, S1PlainDev());
 }
-// same transforms through the 8 KiB half-size transpose buffer
-template <int FV, class C2>
+// ... or the 8 KiB half-size buffer (real parts, then imaginary parts)
+template <class C2>
 __device__ __forceinline__ void warp_fft_fwd_h(int lane, double* xb, const C2& c2, cplx (&v)[32]) {
-    if (fft_opts<FV>::f1) dft32_fwd_tan<kP1Center, kP1MinLevel>(v, S1Dev());
-    else dft32_fwd(v, S1PlainDev());
+    dft32_fwd(v, S1PlainDev());
     xpose_store_fwd_h(lane, xb, v, 0);
     __syncwarp();
     xpose_load_fwd_h(lane, xb, v, 0);      // v[].x: transposed real parts; v[].y: still the untransposed imaginary parts
@@ -83,11 +69,11 @@ __device__ __forceinline__ void warp_fft_fwd_h(int lane, double* xb, const C2& c
     __syncwarp();
     xpose_load_fwd_h(lane, xb, v, 1);
     __syncwarp();
-    dft32_fwd_tan<kP2Center, fft_opts<FV>::p2_min_level>(v, c2);
+    dft32_fwd(v, c2);
 }
-template <int FV, int TW_BASE, class C2>
+template <class C2>
 __device__ __forceinline__ void warp_fft_inv_h(int lane, double* xb, const C2& c2, cplx (&v)[32]) {
-    dft32_inv_tan<kP2Center, fft_opts<FV>::p2_min_level>(v, c2);
+    dft32_inv(v, c2);
     xpose_store_inv_h(lane, xb, v, 0);
     __syncwarp();
     xpose_load_inv_h(lane, xb, v, 0);
@@ -96,21 +82,13 @@ __device__ __forceinline__ void warp_fft_inv_h(int lane, double* xb, const C2& c
     __syncwarp();
     xpose_load_inv_h(lane, xb, v, 1);
     __syncwarp();
-    if (fft_opts<FV>::i1) idft32_dit_twist(v, S1Dev(), TW_BASE);
-    else dft32_inv(v, S1PlainDev());
+    dft32_inv(v, S1PlainDev());
 }
-template <int FV, typename AccT>
-__device__ __forceinline__ void tail_fv(int lane, pair_t<AccT>* acc, const cplx (&v)[32]) {
-    if (fft_opts<FV>::i1) cmux_tail_scaled<AccT>(lane, acc, v);
-    else cmux_tail<AccT>(lane, acc, v);
-}
-constexpr int kDefaultFV = 0;
 __device__ __forceinline__ void warp_fft_fwd(int lane, cplx* xbuf, const cplx (&s2)[16], cplx (&v)[32]) {
-    warp_fft_fwd_c<kDefaultFV>(lane, xbuf, RegConsts(s2), v);
+    warp_fft_fwd_c(lane, xbuf, RegConsts(s2), v);
 }
-template <int TW_BASE>
 __device__ __forceinline__ void warp_fft_inv(int lane, cplx* xbuf, const cplx (&s2)[16], cplx (&v)[32]) {
-    warp_fft_inv_c<kDefaultFV, TW_BASE>(lane, xbuf, RegConsts(s2), v);
+    warp_fft_inv_c(lane, xbuf, RegConsts(s2), v);
 }
 // per-lane pass-2 constants kept in a shared-memory table [16][32] instead of 32 registers
 struct SmemLaneConsts {
@@ -134,7 +112,7 @@ __global__ void __launch_bounds__(32) bsk_convert_kernel(const uint64_t* __restr
     const int i = blockIdx.x >> 2, g = blockIdx.x & 3;
     const uint64_t* src = bsk + (size_t)blockIdx.x * kN;
     cplx s2[16];
-    lane_consts_tan(4 * lane + 1, kP2Center, fft_opts<kDefaultFV>::p2_min_level, s2);
+    lane_consts(4 * lane + 1, s2);
     cplx v[32];
 #pragma unroll
     for (int j2 = 0; j2 < 32; ++j2) {
@@ -174,7 +152,7 @@ __global__ void __launch_bounds__(64, 4) pbs_pair_kernel(const cplx* __restrict_
     const uint64_t* lut = luts + (size_t)(lut_idx ? lut_idx[c] : 0) * kN;
 
     cplx s2[16];
-    lane_consts_tan(4 * lane + 1, kP2Center, fft_opts<kDefaultFV>::p2_min_level, s2);
+    lane_consts(4 * lane + 1, s2);
 
     // accumulator <- (0, X^{-b} * LUT)
     {
@@ -223,8 +201,8 @@ __global__ void __launch_bounds__(64, 4) pbs_pair_kernel(const cplx* __restrict_
         }
         __syncthreads();
 
-        warp_fft_inv<uni_tw<AccT>::base>(lane, xbuf, s2, X);
-        tail_fv<kDefaultFV, AccT>(lane, acc, X);
+        warp_fft_inv(lane, xbuf, s2, X);
+        cmux_tail<AccT>(lane, acc, X);
         __syncwarp();
     }
     __syncthreads();
@@ -243,18 +221,18 @@ __global__ void __launch_bounds__(64, 4) pbs_pair_kernel(const cplx* __restrict_
 //                full[NCH], empty[NCH] mbarriers
 // ---------------------------------------------------------------------------------------
 
-template <typename AccT, int CTS, int NCH, bool S2S, int FV, bool XH, bool HS>
+template <typename AccT, int CTS, int NCH, bool XH, bool HS>
 __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                                      int n, int base_log, const uint64_t* __restrict__ luts,
                                                                      const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
-                                                                     const int32_t* __restrict__ out_idx, int count, int stagger) {
+                                                                     const int32_t* __restrict__ out_idx, int count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pair_t<AccT>* acc_all = reinterpret_cast<pair_t<AccT>*>(smem_raw);
     constexpr int kXb = XH ? 512 : 1024;                 // transpose / exchange buffer per warp, in complex units
     cplx* xbuf_all = reinterpret_cast<cplx*>(smem_raw + (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>));
     cplx* ring = xbuf_all + (size_t)CTS * 2 * kXb;
     cplx* s2tab = ring + (size_t)NCH * (HS ? kHalfCplx : kChunkCplx);
-    uint64_t* full = reinterpret_cast<uint64_t*>(s2tab + (S2S ? 16 * 32 : 0));
+    uint64_t* full = reinterpret_cast<uint64_t*>(s2tab + 16 * 32);
     uint64_t* empty = full + NCH;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -294,23 +272,18 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
     const uint64_t* ct = in_small + (size_t)c * (n + 1);
     const uint64_t* lut = luts + (size_t)(lut_idx ? lut_idx[c] : 0) * kN;
 
-    cplx s2[S2S ? 1 : 16];
-    if (S2S) {
-        if (warp == 0) {
-            cplx tmp[16];
-            if (HS) {      // pass32 form: (re, im) for the first level, (cos, tan) below
+    if (warp == 0) {      // per-lane pass-2 constants, g = 4 lane + 1
+        cplx tmp[16];
+        if (HS) {      // pass32 form: (re, im) for the first level, (cos, tan) below
 #pragma unroll
-                for (int ci = 0; ci < 16; ++ci) tmp[ci] = pass_const(ci, 4 * lane + 1);
-            } else {
-                lane_consts_tan(4 * lane + 1, kP2Center, fft_opts<FV>::p2_min_level, tmp);
-            }
-#pragma unroll
-            for (int ci = 0; ci < 16; ++ci) s2tab[ci * 32 + lane] = tmp[ci];
+            for (int ci = 0; ci < 16; ++ci) tmp[ci] = pass_const(ci, 4 * lane + 1);
+        } else {
+            lane_consts(4 * lane + 1, tmp);
         }
-        __syncthreads();
-    } else {
-        lane_consts_tan(4 * lane + 1, kP2Center, fft_opts<FV>::p2_min_level, reinterpret_cast<cplx(&)[16]>(s2));
+#pragma unroll
+        for (int ci = 0; ci < 16; ++ci) s2tab[ci * 32 + lane] = tmp[ci];
     }
+    __syncthreads();
     const SmemLaneConsts c2s{s2tab + lane};
     {
         const int b = modswitch(ct[n]);
@@ -320,16 +293,6 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
             pair_t<AccT> z; z.x = 0; z.y = 0;
             acc[idx] = p ? lut_pair<AccT>(lut, idx, b) : z;
         }
-    }
-    __syncwarp();
-
-    // De-phase the ciphertexts of the CTA: identical code on identical data keeps all warps in the same phase
-    // (all in shared-memory traffic or all in FP64 work at once); a start offset of ctl * stagger cycles lets the
-    // FP64 phases of one ciphertext overlap the transpose / exchange phases of the others.  Needs a ring deep
-    // enough to hold the spread (the XH configuration).
-    if (stagger > 0 && ctl > 0) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < (long long)ctl * stagger) { }
     }
     __syncwarp();
 
@@ -356,15 +319,13 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
             xpose_load_fwd_h(lane, xb, X, 1);
             __syncwarp();
             pass32(X, c2s);
-        } else if (XH) warp_fft_fwd_h<FV>(lane, reinterpret_cast<double*>(xbuf), c2s, X);
-        else if (S2S) warp_fft_fwd_c<FV>(lane, xbuf, c2s, X);
-        else warp_fft_fwd_c<FV>(lane, xbuf, RegConsts(reinterpret_cast<cplx(&)[16]>(s2)), X);
+        } else if (XH) warp_fft_fwd_h(lane, reinterpret_cast<double*>(xbuf), c2s, X);
+        else warp_fft_fwd_c(lane, xbuf, c2s, X);
 
         if constexpr (HS) {
             // Half-step product (same order as pbs_stream_kernel): the own-spectrum products run between the exchange
             // store and the pair barrier, so the wait for the partner hides behind 64 FMAs; one barrier wait and one
             // arrive per 32 KB key half.
-            static_assert(!HS || XH, "half-step ring needs the half-size exchange buffer");
             if (hs_producer) {
                 while (hprod.next_h < 2 * (i + 1) && hprod.next_h < 2 * n) hprod.poll(lane, bsk_f, ring, full, empty, 2 * n);
             }
@@ -409,9 +370,8 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
                 xpose_load_inv_h(lane, xb, X, 1);
                 __syncwarp();
             }
-            if (fft_opts<FV>::i1) idft32_dit_twist(X, S1Dev(), uni_tw<AccT>::base);
-            else dft32_inv(X, S1PlainDev());
-            tail_fv<FV, AccT>(lane, acc, X);
+            dft32_inv(X, S1PlainDev());
+            cmux_tail<AccT>(lane, acc, X);
             __syncwarp();
             if (hs_producer) hprod.poll(lane, bsk_f, ring, full, empty, 2 * n);
             continue;
@@ -454,10 +414,9 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
             pair_barrier(1 + ctl);
         }
 
-        if (XH) warp_fft_inv_h<FV, uni_tw<AccT>::base>(lane, reinterpret_cast<double*>(xbuf), c2s, X);
-        else if (S2S) warp_fft_inv_c<FV, uni_tw<AccT>::base>(lane, xbuf, c2s, X);
-        else warp_fft_inv_c<FV, uni_tw<AccT>::base>(lane, xbuf, RegConsts(reinterpret_cast<cplx(&)[16]>(s2)), X);
-        tail_fv<FV, AccT>(lane, acc, X);
+        if (XH) warp_fft_inv_h(lane, reinterpret_cast<double*>(xbuf), c2s, X);
+        else warp_fft_inv_c(lane, xbuf, c2s, X);
+        cmux_tail<AccT>(lane, acc, X);
         __syncwarp();
     }
     pair_barrier(1 + ctl);
@@ -478,7 +437,7 @@ __global__ void __launch_bounds__(32) negacyclic_mul_kernel(const uint64_t* __re
     const int lane = threadIdx.x;
     a += (size_t)blockIdx.x * kN; b += (size_t)blockIdx.x * kN; c += (size_t)blockIdx.x * kN;
     cplx s2[16];
-    lane_consts_tan(4 * lane + 1, kP2Center, fft_opts<kDefaultFV>::p2_min_level, s2);
+    lane_consts(4 * lane + 1, s2);
     cplx va[32], vb[32];
 #pragma unroll
     for (int j2 = 0; j2 < 32; ++j2) {
@@ -494,11 +453,11 @@ __global__ void __launch_bounds__(32) negacyclic_mul_kernel(const uint64_t* __re
         va[r].x = x.x * y.x - x.y * y.y; va[r].y = x.x * y.y + x.y * y.x;
     }
     __syncwarp();
-    warp_fft_inv<kUniTw64>(lane, xbuf, s2, va);
+    warp_fft_inv(lane, xbuf, s2, va);
 #pragma unroll
     for (int j2 = 0; j2 < 32; ++j2) {
-        c[lane + 32 * j2] = fft_opts<kDefaultFV>::i1 ? to_acc_scaled<uint64_t>(va[j2].x) : to_acc<uint64_t>(va[j2].x);
-        c[lane + 32 * j2 + 1024] = fft_opts<kDefaultFV>::i1 ? to_acc_scaled<uint64_t>(va[j2].y) : to_acc<uint64_t>(va[j2].y);
+        c[lane + 32 * j2] = to_acc<uint64_t>(va[j2].x);
+        c[lane + 32 * j2 + 1024] = to_acc<uint64_t>(va[j2].y);
     }
 }
 
@@ -522,21 +481,19 @@ static void launch_pbs_pair_t(const void* bsk_f, const uint64_t* in_small, int n
                                                     lut_idx, out_big, out_idx, count);
 }
 
-template <typename AccT, int CTS, int NCH, bool S2S, int FV, bool XH = false, bool HS = false>
+template <typename AccT, int CTS, int NCH, bool XH, bool HS>
 static void launch_pbs_ring_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
                               const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     const size_t smem = (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>) + (size_t)CTS * 2 * (XH ? 512 : 1024) * sizeof(cplx) +
-                        (size_t)NCH * (HS ? kHalfCplx : kChunkCplx) * sizeof(cplx) + (S2S ? 16 * 32 * sizeof(cplx) : 0) + 2 * NCH * sizeof(uint64_t);
+                        (size_t)NCH * (HS ? kHalfCplx : kChunkCplx) * sizeof(cplx) + 16 * 32 * sizeof(cplx) + 2 * NCH * sizeof(uint64_t);
     static bool configured = false;
     if (!configured) {
-        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_ring_kernel<AccT, CTS, NCH, S2S, FV, XH, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_ring_kernel<AccT, CTS, NCH, XH, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    static int stagger = -1;
-    if (stagger < 0) { const char* e = getenv("FSC_PBS_STAGGER"); stagger = e ? atoi(e) : 0; }
     const int grid = (count + CTS - 1) / CTS;
-    pbs_ring_kernel<AccT, CTS, NCH, S2S, FV, XH, HS><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log,
-                                                                        luts, lut_idx, out_big, out_idx, count, stagger);
+    pbs_ring_kernel<AccT, CTS, NCH, XH, HS><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log,
+                                                                        luts, lut_idx, out_big, out_idx, count);
 }
 
 // Which blind-rotation kernel a context uses (fixed at key upload, because the Fourier key layout differs):
@@ -563,7 +520,7 @@ void launch_pbs(int variant, int acc_bits, const void* bsk_f, const uint64_t* in
     // ring kernel, half-step key ring (NH stages of 32 KB): wide levels pack 4 (u32 accumulator) or 3 (u64) ciphertexts
     // per CTA so that one key copy feeds them all; levels of at most one or two ciphertexts per SM use 1 or 2 per CTA
 #define FSC_RING(ACC, CTS, NH) \
-    launch_pbs_ring_t<ACC, CTS, NH, true, 0, true, true>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st)
+    launch_pbs_ring_t<ACC, CTS, NH, true, true>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st)
     if (variant == 0) {      // variants 1 and 3 use the ring kernel here
         if (acc_bits == 32) launch_pbs_pair_t<uint32_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
         else launch_pbs_pair_t<uint64_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
@@ -575,7 +532,7 @@ void launch_pbs(int variant, int acc_bits, const void* bsk_f, const uint64_t* in
         // 64-bit accumulator: the chunked ring (8 KB chunks, blocking producer) measures faster than the half-step ring
         // here (47.0 k against 42.1 k PBS/s at 4096 blocks)
 #define FSC_RING_CHUNKED(CTS, NCH, XH) \
-    launch_pbs_ring_t<uint64_t, CTS, NCH, true, 0, XH, false>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st)
+    launch_pbs_ring_t<uint64_t, CTS, NCH, XH, false>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st)
         if (count <= sm_count) FSC_RING_CHUNKED(1, 10, false);
         else if (count <= 2 * sm_count) FSC_RING_CHUNKED(2, 10, false);
         else FSC_RING_CHUNKED(3, 9, true);

@@ -20,9 +20,9 @@ def emu():
         subprocess.check_call(["/usr/bin/g++", "-O2", "-march=x86-64-v3", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
     E = C.CDLL(so)
     vp = C.c_void_p
-    E.emu_negacyclic_mul.argtypes = [vp, vp, vp]
+    E.emu_negacyclic_mul.argtypes = [C.c_int, vp, vp, vp]
     E.emu_convert_bsk.argtypes = [C.c_int, vp, vp]
-    E.emu_blind_rotate.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
+    E.emu_blind_rotate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
     E.emu_init()
     return E
 
@@ -31,17 +31,19 @@ def P(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def test_emu_fft_matches_exact_product(emu, orc, rng):
+@pytest.mark.parametrize("form", [0, 1])
+def test_emu_fft_matches_exact_product(emu, orc, rng, form):
+    """form 0: plain constants (64-bit accumulator ring, pair kernel); form 1: the half-step ring's tangent-form passes."""
     a = rng.integers(0, 2**64, 2048, dtype=np.uint64)
     b = rng.integers(-2**22, 2**22, 2048, dtype=np.int64)
     c = np.empty_like(a)
-    emu.emu_negacyclic_mul(P(a), P(b), P(c))
+    emu.emu_negacyclic_mul(form, P(a), P(b), P(c))
     d = (c - orc.negacyclic_mul_exact(a, b)).astype(np.int64)
     assert np.abs(d).max() < 2**43
 
 
-@pytest.mark.parametrize("acc_bits", [64, 32])
-def test_emu_blind_rotation_decrypts_like_oracle(emu, orc, oracle_keys, rng, acc_bits):
+@pytest.mark.parametrize("acc_bits,form", [(64, 0), (32, 1)])
+def test_emu_blind_rotation_decrypts_like_oracle(emu, orc, oracle_keys, rng, acc_bits, form):
     K = oracle_keys("toy")
     n = K.params.lwe_dim
     bf = np.empty(n * 32 * 4 * 32 * 2, dtype=np.float64)
@@ -51,7 +53,7 @@ def test_emu_blind_rotation_decrypts_like_oracle(emu, orc, oracle_keys, rng, acc
     m = rng.integers(0, 16, 48).astype(np.uint64)
     small = K.keyswitch(K.encrypt_msgs(m))
     out = np.empty((m.size, 2049), dtype=np.uint64)
-    emu.emu_blind_rotate(acc_bits, n, K.params.pbs_base_log, P(bf), P(small), m.size, P(lut), P(out))
+    emu.emu_blind_rotate(acc_bits, form, n, K.params.pbs_base_log, P(bf), P(small), m.size, P(lut), P(out))
     ref = K.pbs(small, lut)
     assert (K.decrypt_msgs(out) == table[m]).all()
     assert (K.decrypt_msgs(ref) == table[m]).all()
