@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
         // a == 0 is not skipped: the ring is shared by all ciphertexts of the CTA; the step is an exact no-op
 
         cplx X[32];
-        cmux_head<AccT>(lane, acc, a, base_log, X);
+        cmux_head<AccT>(lane, acc, a, base_log, X);      // (the ALU/FMA-split head of pbs_head.cuh measures 3 % slower here)
         if (HS) {      // forward passes in the 6-FMA tangent form (pass32), same node constants as dft32_fwd
             double* xb = reinterpret_cast<double*>(xbuf);
             pass32(X, WT0Dev());
