@@ -98,7 +98,9 @@ EXPORTS = ["fsc_ctx_create", "fsc_ctx_destroy", "fsc_last_error", "fsc_get_param
            "fsc_debug_negacyclic_mul", "fsc_measure_fp64_peak", "fsc_pbs_kernel_name"]
 from .radix import RADIX_EXPORTS  # noqa: E402
 EXPORTS = EXPORTS + RADIX_EXPORTS + ["fsc_client_keygen", "fsc_client_free", "fsc_client_last_error", "fsc_client_server_keys",
-                                     "fsc_client_secret_keys", "fsc_client_encrypt_blocks", "fsc_client_decrypt_blocks"]
+                                     "fsc_client_secret_keys", "fsc_client_encrypt_blocks", "fsc_client_decrypt_blocks",
+                                     "fsc_client_save", "fsc_client_load", "fsc_server_keys_save", "fsc_server_keys_load",
+                                     "fsc_blocks_save", "fsc_blocks_load", "fsc_buffer_free"]
 
 
 def _ptr(a):

@@ -24,7 +24,9 @@ class NoiseParams(C.Structure):
 
 
 CLIENT_EXPORTS = ["fsc_client_keygen", "fsc_client_free", "fsc_client_last_error", "fsc_client_server_keys",
-                  "fsc_client_secret_keys", "fsc_client_encrypt_blocks", "fsc_client_decrypt_blocks"]
+                  "fsc_client_secret_keys", "fsc_client_encrypt_blocks", "fsc_client_decrypt_blocks",
+                  "fsc_client_save", "fsc_client_load", "fsc_server_keys_save", "fsc_server_keys_load",
+                  "fsc_blocks_save", "fsc_blocks_load", "fsc_buffer_free"]
 
 
 def _declare(L):
@@ -36,14 +38,24 @@ def _declare(L):
     L.fsc_client_secret_keys.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.fsc_client_encrypt_blocks.argtypes = [vp, vp, sz, vp]
     L.fsc_client_decrypt_blocks.argtypes = [vp, vp, sz, vp, vp]
+    L.fsc_client_save.argtypes = [vp, C.c_char_p]
+    L.fsc_client_load.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.fsc_server_keys_save.argtypes = [vp, C.c_char_p]
+    L.fsc_server_keys_load.argtypes = [C.c_char_p, C.POINTER(Params), C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]
+    L.fsc_blocks_save.argtypes = [C.c_char_p, C.POINTER(Params), vp, sz]
+    L.fsc_blocks_load.argtypes = [C.c_char_p, C.POINTER(Params), C.POINTER(vp), C.POINTER(sz)]
+    L.fsc_buffer_free.argtypes = [vp]
 
 
 class ClientKey:
     """Secret keys + the server key material derived from them (seeded)."""
 
-    def __init__(self, preset="2_2_gaussian", seed=1):
+    def __init__(self, preset="2_2_gaussian", seed=1, _handle=None, _params=None):
         self.L = load_library()
         _declare(self.L)
+        if _handle is not None:      # ClientKey.load
+            self.h, self.params, self.noise = _handle, _params, None
+            return
         self.params = Params.preset(preset)
         self.noise = NoiseParams(**NOISE[preset])
         h = C.c_void_p()
@@ -63,6 +75,25 @@ class ClientKey:
     def _check(self, rc):
         if rc != 0:
             raise FscError(rc, (self.L.fsc_client_last_error(self.h) or b"").decode())
+
+    # ---- on-disk formats (csrc/keyfile.cpp) ---------------------------------------------------------------
+    def save(self, path):
+        """seeded client key: parameters, noise, seed, secret bits (a few KB; server keys are re-derived on load)."""
+        self._check(self.L.fsc_client_save(self.h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path):
+        L = load_library()
+        _declare(L)
+        h = C.c_void_p()
+        rc = L.fsc_client_load(str(path).encode(), C.byref(h))
+        if rc != 0:
+            raise FscError(rc, (L.fsc_client_last_error(None) or b"").decode())
+        return cls(_handle=h, _params=_file_params(path))
+
+    def save_server_keys(self, path):
+        """expanded bootstrapping + keyswitching keys, no secrets: what the GPU host needs for fsc_keys_upload."""
+        self._check(self.L.fsc_server_keys_save(self.h, str(path).encode()))
 
     def server_keys(self):
         """(bsk_std, ksk) as numpy views, ready for Context.upload_keys."""
@@ -106,6 +137,52 @@ class ClientKey:
         if (d >= 4).any():
             raise ValueError("decrypted block carries are not empty: %s" % d)
         return sum(int(v) << (2 * i) for i, v in enumerate(d))
+
+
+def _file_params(path):
+    """fsc_params stored in an FSCFILE1 container (offset 16, ten u32)."""
+    raw = np.fromfile(str(path), dtype=np.uint32, count=14)[4:14]
+    return Params(*[int(v) for v in raw])
+
+
+def load_server_keys(path):
+    """-> (Params, bsk_std, ksk) from a file written by ClientKey.save_server_keys (copies into numpy arrays)."""
+    L = load_library()
+    _declare(L)
+    p, b, k, nb, nk = Params(), C.c_void_p(), C.c_void_p(), C.c_size_t(), C.c_size_t()
+    rc = L.fsc_server_keys_load(str(path).encode(), C.byref(p), C.byref(b), C.byref(nb), C.byref(k), C.byref(nk))
+    if rc != 0:
+        raise FscError(rc, (L.fsc_client_last_error(None) or b"").decode())
+    try:
+        bsk = np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_uint64)), shape=(nb.value,)).copy()
+        ksk = np.ctypeslib.as_array(C.cast(k, C.POINTER(C.c_uint64)), shape=(nk.value,)).copy()
+    finally:
+        L.fsc_buffer_free(b)
+    return p, bsk, ksk
+
+
+def save_blocks(path, params, blocks):
+    L = load_library()
+    _declare(L)
+    blocks = np.ascontiguousarray(blocks, dtype=np.uint64).reshape(-1, params.glwe_dim * params.poly_size + 1)
+    rc = L.fsc_blocks_save(str(path).encode(), C.byref(params), blocks.ctypes.data_as(C.c_void_p), blocks.shape[0])
+    if rc != 0:
+        raise FscError(rc, (L.fsc_client_last_error(None) or b"").decode())
+
+
+def load_blocks(path):
+    L = load_library()
+    _declare(L)
+    p, b, n = Params(), C.c_void_p(), C.c_size_t()
+    rc = L.fsc_blocks_load(str(path).encode(), C.byref(p), C.byref(b), C.byref(n))
+    if rc != 0:
+        raise FscError(rc, (L.fsc_client_last_error(None) or b"").decode())
+    try:
+        words = p.glwe_dim * p.poly_size + 1
+        out = np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_uint64)), shape=(n.value, words)).copy() if n.value else np.empty((0, words), np.uint64)
+    finally:
+        L.fsc_buffer_free(b)
+    return p, out
 
 
 def generate_keys(preset="2_2_gaussian", seed=1):

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/fhe_sign_cuda.h"
+#include "client_internal.h"
 
 namespace {
 
@@ -110,6 +111,13 @@ static void add_mask_times_key(size_t N, const uint64_t* a, const uint64_t* S, u
         for (size_t j = 0; j < t; ++j) body[j] -= a[j + N - t];
     }
 }
+
+fsc_params fsc_client_params(const fsc_client* c) { return c->p; }
+fsc_noise_params fsc_client_noise(const fsc_client* c) { return c->np; }
+uint64_t fsc_client_seed(const fsc_client* c) { return c->seed; }
+uint64_t fsc_client_enc_counter(const fsc_client* c) { return c->enc_counter; }
+void fsc_client_set_enc_counter(fsc_client* c, uint64_t v) { c->enc_counter = v; }
+void fsc_client_set_error(const std::string& msg) { g_client_error = msg; }
 
 extern "C" {
 

@@ -199,6 +199,21 @@ fsc_status fsc_client_encrypt_blocks(fsc_client *c, const uint8_t *values, size_
 /* values: decoded plaintext incl. the padding bit (0..31); noise (optional): signed phase error per block */
 fsc_status fsc_client_decrypt_blocks(fsc_client *c, const uint64_t *blocks, size_t n_blocks, uint8_t *values, int64_t *noise);
 
+/* ---- on-disk formats (host CPU; container layout documented in csrc/keyfile.cpp and INTEGRATION.md) ----
+ * Replaces nothing in the reference, which regenerates keys in every test (src/biguint.rs:277); a deployment keeps
+ * the client key (parameters + noise + seed + secret bits, a few KB: the 123 MB of server key material are re-derived
+ * from the seed on load) on the signer's side and ships the expanded server key, without secrets, to the GPU host. */
+fsc_status fsc_client_save(const fsc_client *c, const char *path);
+fsc_status fsc_client_load(const char *path, fsc_client **out);
+fsc_status fsc_server_keys_save(const fsc_client *c, const char *path);
+/* bsk and ksk point into ONE allocation: release it with fsc_buffer_free(*bsk)                               */
+fsc_status fsc_server_keys_load(const char *path, fsc_params *params, uint64_t **bsk, size_t *bsk_words,
+                                uint64_t **ksk, size_t *ksk_words);
+/* big LWE blocks (radix digits), n_blocks x (k N + 1) words                                                  */
+fsc_status fsc_blocks_save(const char *path, const fsc_params *params, const uint64_t *blocks, size_t n_blocks);
+fsc_status fsc_blocks_load(const char *path, fsc_params *params, uint64_t **blocks, size_t *n_blocks);
+fsc_status fsc_buffer_free(uint64_t *buffer);
+
 /* ---- measurement & test hooks ---------------------------------------------------------- */
 /* CUDA-event timer on the context's stream.                                                      */
 fsc_status fsc_timer_start(fsc_ctx *ctx);

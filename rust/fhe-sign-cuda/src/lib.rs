@@ -39,6 +39,10 @@ pub mod sys {
         pub fn fsc_radix_binary(ctx: *mut fsc_ctx, op: u32, a: *const fsc_radix, b: *const fsc_radix, out: *mut *mut fsc_radix) -> i32;
         pub fn fsc_radix_scalar(ctx: *mut fsc_ctx, op: u32, a: *const fsc_radix, s: *const u8, n_bytes: usize, out: *mut *mut fsc_radix) -> i32;
         pub fn fsc_radix_cast(ctx: *mut fsc_ctx, a: *const fsc_radix, n_blocks: usize, out: *mut *mut fsc_radix) -> i32;
+        // on-disk formats (csrc/keyfile.cpp): expanded server key written by the signer's side, read by the GPU host
+        pub fn fsc_server_keys_load(path: *const c_char, params: *mut fsc_params, bsk: *mut *mut u64, bsk_words: *mut usize,
+                                    ksk: *mut *mut u64, ksk_words: *mut usize) -> i32;
+        pub fn fsc_buffer_free(buffer: *mut u64) -> i32;
     }
     pub const OP_ADD: u32 = 0; pub const OP_MUL: u32 = 2; pub const OP_MIN: u32 = 3; pub const OP_SHR: u32 = 5;
     pub const OP_AND: u32 = 7; pub const OP_DIV: u32 = 12;
@@ -63,6 +67,21 @@ fn check(key: &GpuServerKey, rc: i32) {
 }
 
 impl GpuServerKey {
+    /// Server key from an FSCFILE1 container written by `fsc_server_keys_save` (no secrets inside).
+    pub fn from_file(path: &str, device: i32) -> Result<Self, String> {
+        let c = std::ffi::CString::new(path).map_err(|e| e.to_string())?;
+        let mut p = sys::fsc_params { lwe_dim: 0, glwe_dim: 0, poly_size: 0, pbs_base_log: 0, pbs_level: 0, ks_base_log: 0,
+                                      ks_level: 0, message_modulus: 0, carry_modulus: 0, acc_bits: 0 };
+        let (mut bsk, mut ksk) = (std::ptr::null_mut(), std::ptr::null_mut());
+        let (mut nb, mut nk) = (0usize, 0usize);
+        let rc = unsafe { sys::fsc_server_keys_load(c.as_ptr(), &mut p, &mut bsk, &mut nb, &mut ksk, &mut nk) };
+        if rc != 0 { return Err(format!("fsc_server_keys_load failed with status {}", rc)); }
+        p.acc_bits = 32;
+        let key = unsafe { Self::new(p, device, std::slice::from_raw_parts(bsk, nb), std::slice::from_raw_parts(ksk, nk)) };
+        unsafe { sys::fsc_buffer_free(bsk); }
+        key
+    }
+
     /// `bsk`: standard-domain bootstrapping key, `ksk`: keyswitching key, as exported by the client-side keygen.
     pub fn new(params: sys::fsc_params, device: i32, bsk: &[u64], ksk: &[u64]) -> Result<Self, String> {
         let mut ctx = std::ptr::null_mut();

@@ -63,3 +63,58 @@ def test_bootstrapping_key_rows_encrypt_the_small_key_bits(ck, orc):
                     want[0] = fac
             err = (phase - want).astype(np.int64)
             assert np.abs(err).max() < 2**22, (i, p)
+
+
+# ---- on-disk formats (csrc/keyfile.cpp) ----
+
+def test_client_key_file_roundtrip(ck, tmp_path):
+    """the seeded client key file re-derives the same secret and server keys and never replays encryption randomness."""
+    from fhe_sign_b200.client import ClientKey
+    vals = np.arange(16, dtype=np.uint8)
+    ct_before = ck.encrypt_block_values(vals)
+    path = tmp_path / "client.fsc"
+    ck.save(path)
+    assert path.stat().st_size < 64 * 1024                       # parameters + seed + secret bits, not 123 MB
+    ck2 = ClientKey.load(path)
+    assert ck2.params.lwe_dim == ck.params.lwe_dim and ck2.params.pbs_base_log == ck.params.pbs_base_log
+    for a, b in zip(ck.secret_keys(), ck2.secret_keys()):
+        assert np.array_equal(a, b)
+    for a, b in zip(ck.server_keys(), ck2.server_keys()):
+        assert np.array_equal(a, b)
+    assert (ck2.decrypt_block_values(ct_before) == vals).all()   # old ciphertexts decrypt under the loaded key
+    ct_after = ck2.encrypt_block_values(vals)
+    assert (ck.decrypt_block_values(ct_after) == vals).all()
+    assert not np.array_equal(ct_after, ct_before)               # the encryption counter travelled with the file
+
+
+def test_server_key_and_block_files_roundtrip_and_reject_corruption(ck, tmp_path):
+    from fhe_sign_b200.capi import FscError
+    from fhe_sign_b200.client import load_blocks, load_server_keys, save_blocks
+    path = tmp_path / "server.fsc"
+    ck.save_server_keys(path)
+    p, bsk, ksk = load_server_keys(path)
+    assert p.lwe_dim == ck.params.lwe_dim and p.ks_level == ck.params.ks_level
+    assert np.array_equal(bsk, ck.server_keys()[0]) and np.array_equal(ksk, ck.server_keys()[1])
+    ct = ck.encrypt_block_values(np.arange(12, dtype=np.uint8))
+    bpath = tmp_path / "ct.fsc"
+    save_blocks(bpath, ck.params, ct)
+    p2, ct2 = load_blocks(bpath)
+    assert p2.poly_size == 2048 and np.array_equal(ct, ct2)
+    save_blocks(tmp_path / "empty.fsc", ck.params, np.empty((0, 2049), np.uint64))
+    assert load_blocks(tmp_path / "empty.fsc")[1].shape == (0, 2049)
+    # a flipped payload byte, a truncated file, the wrong kind and a foreign file are all refused
+    raw = bytearray(bpath.read_bytes())
+    raw[200] ^= 1
+    (tmp_path / "bad.fsc").write_bytes(bytes(raw))
+    with pytest.raises(FscError, match="checksum"):
+        load_blocks(tmp_path / "bad.fsc")
+    (tmp_path / "short.fsc").write_bytes(bpath.read_bytes()[:-100])
+    with pytest.raises(FscError):
+        load_blocks(tmp_path / "short.fsc")
+    with pytest.raises(FscError, match="kind"):
+        load_server_keys(bpath)
+    (tmp_path / "foreign.fsc").write_bytes(b"not a key file" * 20)
+    with pytest.raises(FscError, match="FSCFILE1"):
+        load_blocks(tmp_path / "foreign.fsc")
+    with pytest.raises(FscError):
+        load_blocks(tmp_path / "missing.fsc")
