@@ -32,7 +32,7 @@ class Params(C.Structure):
     }
 
     @classmethod
-    def preset(cls, name, acc_bits=64):
+    def preset(cls, name, acc_bits=32):
         d = dict(glwe_dim=1, poly_size=2048, pbs_level=1, ks_base_log=3, ks_level=5,
                  message_modulus=4, carry_modulus=4, acc_bits=acc_bits)
         d.update(cls.PRESETS[name])

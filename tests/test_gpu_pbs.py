@@ -193,6 +193,32 @@ def test_error_codes(gpu_ctx, oracle_keys):
     ctx.close()
 
 
+def test_stream_kernel_noise_statistics(oracle_keys, monkeypatch):
+    """the stream kernel forced for every width (FSC_PBS_VARIANT=stream): sigma of fresh PBS outputs over 25 600 real
+    bootstraps of the 2_2 parameter set inside the same budget as the default kernels, zero decode failures."""
+    import fhe_sign_b200 as fsb
+    monkeypatch.setenv("FSC_PBS_VARIANT", "stream")
+    K = oracle_keys("2_2_gaussian")
+    ctx = fsb.Context(fsb.Params.preset("2_2_gaussian", acc_bits=32))
+    ctx.upload_keys(K.bsk, K.ksk)
+    assert ctx.pbs_kernel_name() == "pbs_stream_kernel"
+    table = (np.arange(16) * 7 + 3) % 16
+    luts = ctx.luts_from_tables(table)
+    rng = np.random.default_rng(6)
+    total, chunk, sq, fails = 25600, 6400, 0.0, 0
+    for s in range(total // chunk):
+        m = rng.integers(0, 16, chunk).astype(np.uint64)
+        out = ctx.apply_lut_host(K.encrypt_msgs(m, seed=12, stream=s * chunk), luts)
+        exp = table[m].astype(np.uint64)
+        fails += int((K.decrypt_msgs(out) != exp).sum())
+        e = _noise(K, out, exp)
+        sq += float((e * e).sum())
+    sigma = (sq / total) ** 0.5
+    print("stream kernel sigma_pbs=2^%.3f over %d bootstraps" % (np.log2(sigma), total))
+    assert fails == 0 and sigma < 2.0**-14.0
+    ctx.close()
+
+
 @pytest.mark.parametrize("acc_bits", [64, 32])
 def test_noise_over_1e5_bootstraps(gpu_ctx, oracle_keys, acc_bits):
     """north_star: PBS noise within the parameter set's variance bound over >= 1e5 bootstraps.
