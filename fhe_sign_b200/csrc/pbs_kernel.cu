@@ -3,10 +3,15 @@
 // Kernels:
 //   bsk_convert_kernel   standard-domain bootstrapping key -> Fourier domain, in the exact
 //                        (register position, lane) order the blind rotation consumes
-//   pbs_pair_kernel      two warps per ciphertext (one per GLWE polynomial): modulus switch,
-//                        accumulator init from the LUT, n CMUX steps (pbs_core.cuh), sample
-//                        extraction of coefficient 0
-//   negacyclic_mul_kernel / fft_roundtrip hooks for the parity tests
+//   pbs_ring_kernel      the wide-batch kernel: CTS ciphertexts per CTA, two warps each (one per GLWE
+//                        polynomial); modulus switch, accumulator init from the LUT, n CMUX steps with the
+//                        Fourier GGSW streamed through a TMA-fed shared-memory ring, sample extraction of
+//                        coefficient 0.  Two configurations: half-step ring + tangent-form forward passes
+//                        (32-bit accumulator), chunked ring + plain passes (64-bit accumulator)
+//   pbs_pair_kernel      first version (one ciphertext per CTA, key straight from L2), kept as
+//                        FSC_PBS_VARIANT=pair for comparison
+//   negacyclic_mul_kernel  test hook; fp64_peak_kernel: the roofline probe
+// (pbs_stream_kernel.cu holds the second blind-rotation kernel, used for narrow levels)
 //
 // Replaces (concept): tfhe 0.10.0 programmable_bootstrap_lwe_ciphertext (Cargo.lock:482-485), the
 // PBS half of shortint apply_lookup_table behind every operator in src/biguint.rs:110-248.
@@ -212,13 +217,18 @@ __global__ void __launch_bounds__(64, 4) pbs_pair_kernel(const cplx* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------
-// Ring variant: one CTA = CTS ciphertexts (2 warps each).  The Fourier GGSW of every CMUX step is
+// Ring kernel: one CTA = CTS ciphertexts (2 warps each).  The Fourier GGSW of every CMUX step is
 // streamed from L2 into a shared-memory ring by 1-D bulk copies (TMA, cp.async.bulk + mbarrier
-// complete_tx) issued NCH-1 chunks ahead of use by one elected lane of warp 0, so that the
-// Fourier-domain product reads the key from shared memory instead of waiting on L2 latency, and one
-// L2 read feeds all CTS ciphertexts of the CTA.
-// shared memory: acc [CTS][2][1024] pair_t<AccT> | xbuf [CTS][2][1024] cplx | ring [NCH][512] cplx |
-//                full[NCH], empty[NCH] mbarriers
+// complete_tx), so that the Fourier-domain product reads the key from shared memory instead of
+// waiting on L2 latency, and one L2 read feeds all CTS ciphertexts of the CTA.
+//   HS  (32-bit accumulator): NCH half-step stages of 32 KiB, non-blocking producer in warp 0 a whole
+//       step ahead (tma_ring.cuh HalfProducer); own-spectrum products before the pair barrier;
+//       forward passes pass32 (6-FMA tangent form), inverse pass 2 pass32_inv_gs
+//   !HS (64-bit accumulator): NCH chunks of 8 KiB, one elected lane of warp 0 issues 3 chunks ahead and
+//       blocks on the release of the stage it refills; plain (re, im) passes
+// XH: 8 KiB half-size transpose / exchange buffer per warp (real parts, then imaginary parts).
+// shared memory: acc [CTS][2][1024] pair_t<AccT> | xbuf [CTS][2][XH ? 512 : 1024] cplx | ring |
+//                s2tab [16][32] cplx (per-lane pass-2 constants) | full[NCH], empty[NCH] mbarriers
 // ---------------------------------------------------------------------------------------
 
 template <typename AccT, int CTS, int NCH, bool XH, bool HS>
