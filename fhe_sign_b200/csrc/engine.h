@@ -27,7 +27,7 @@ struct Engine {
     uint8_t* ksk_limbs = nullptr;   // byte-limb transpose of the KSK for the tensor-core keyswitch [8(n+1) padded][kN*l_ks]
     int8_t* ks_digits = nullptr;    // digit matrix of the current batch [rows padded to 128][kN*l_ks]
     size_t ks_digits_cap = 0;
-    int ks_variant = 1;             // 0 = CUDA-core kernel, 1 = tensor-core (mma.sync s8 x u8) kernel
+    int ks_variant = 2;             // 0 = CUDA-core kernel, 1 = mma.sync s8 x u8 limb GEMM, 2 = tcgen05 kind::i8 limb GEMM (default)
     uint64_t* scratch_small = nullptr;   // keyswitch outputs of the current batch
     uint32_t* scratch_idx = nullptr;     // LUT indices of the current batch
     size_t scratch_cap = 0;

@@ -56,7 +56,7 @@ Engine::Engine(const fsc_params& prm, int device, uintptr_t ext_stream) : p(prm)
     FSC_CUDA_CHECK(cudaEventCreate(&ev1));
     pbs_init_constants();
     const char* kv = getenv("FSC_KS_VARIANT");      // "simt" | "mma" (default)
-    ks_variant = (kv && kv[0] == 's') ? 0 : 1;
+    ks_variant = (kv && kv[0] == 's') ? 0 : (kv && kv[0] == 'm') ? 1 : 2;      // simt | mma | umma (default)
 }
 
 Engine::~Engine() {
@@ -160,7 +160,7 @@ const uint32_t* Engine::stage_lut_idx(const uint32_t* lut_idx, size_t count, con
 void Engine::keyswitch(const uint64_t* in_big, uint64_t* out_small, size_t count) {
     use();
     if (!ksk) throw Error(FSC_ERR_NO_KEYS, "server keys not uploaded");
-    if (ks_variant == 1) {
+    if (ks_variant >= 1) {
         const size_t rows = ks_mma_digit_rows(count), K = (size_t)p.poly_size * p.ks_level;
         if (rows > ks_digits_cap) {
             FSC_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -169,8 +169,15 @@ void Engine::keyswitch(const uint64_t* in_big, uint64_t* out_small, size_t count
             FSC_CUDA_CHECK(cudaMalloc(&ks_digits, rows * K));
             ks_digits_cap = rows;
         }
-        launch_keyswitch_mma(ksk_limbs, ks_digits, in_big, out_small, (int)count, (int)p.poly_size, (int)p.lwe_dim,
-                             (int)p.ks_base_log, (int)p.ks_level, stream);
+        if (ks_variant == 2) {
+            FSC_REQUIRE(p.ks_base_log <= 7 && p.ks_base_log * p.ks_level < 64, "keyswitch (tensor-core path): unsupported decomposition");
+            launch_ks_decompose(in_big, ks_digits, (int)count, (int)rows, (int)p.poly_size, (int)p.ks_base_log, (int)p.ks_level, stream);
+            launch_keyswitch_umma(ksk_limbs, ks_mma_limb_rows((int)p.lwe_dim), ks_digits, (int)rows, in_big, out_small, (int)count,
+                                  (int)p.poly_size, (int)p.lwe_dim, (int)p.ks_level, stream);
+        } else {
+            launch_keyswitch_mma(ksk_limbs, ks_digits, in_big, out_small, (int)count, (int)p.poly_size, (int)p.lwe_dim,
+                                 (int)p.ks_base_log, (int)p.ks_level, stream);
+        }
         launches += 2;
     } else {
         launch_keyswitch(ksk, in_big, out_small, (int)count, (int)p.poly_size, (int)p.lwe_dim, (int)p.ks_base_log,

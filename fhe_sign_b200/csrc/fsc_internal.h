@@ -55,6 +55,11 @@ void launch_keyswitch(const uint64_t* ksk, const uint64_t* in_big, uint64_t* out
 size_t ks_mma_limb_rows(int n);
 size_t ks_mma_digit_rows(size_t count);
 void launch_ksk_limb_transpose(const uint64_t* ksk, uint8_t* out, int K, int n, cudaStream_t st);
+void launch_ks_decompose(const uint64_t* in_big, int8_t* digits, int count, int rows_pad, int big_dim, int base_log, int level,
+                         cudaStream_t st);
+// ks_umma_kernel.cu (tcgen05 + TMEM + TMA version of the same GEMM; shares the limb and digit matrices)
+void launch_keyswitch_umma(const uint8_t* limbs, size_t limb_rows, const int8_t* digits, int rows_pad, const uint64_t* in_big,
+                           uint64_t* out_small, int count, int big_dim, int n, int level, cudaStream_t st);
 void launch_keyswitch_mma(const uint8_t* limbs, int8_t* digits, const uint64_t* in_big, uint64_t* out_small, int count,
                           int big_dim, int n, int base_log, int level, cudaStream_t st);
 

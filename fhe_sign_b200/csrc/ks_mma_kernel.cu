@@ -174,13 +174,19 @@ __global__ void __launch_bounds__(MM_THREADS) ks_mma_kernel(const int8_t* __rest
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
-size_t ks_mma_limb_rows(int n) { return (size_t)((8 * (n + 1) + MM_BN - 1) / MM_BN) * MM_BN; }
+// padded to 256 rows: the limb matrix is shared with the tcgen05 kernel (ks_umma_kernel.cu, 256-column tiles)
+size_t ks_mma_limb_rows(int n) { return (size_t)((8 * (n + 1) + 255) / 256) * 256; }
 size_t ks_mma_digit_rows(size_t count) { return (count + MM_BM - 1) / MM_BM * MM_BM; }
 
 void launch_ksk_limb_transpose(const uint64_t* ksk, uint8_t* out, int K, int n, cudaStream_t st) {
     const int row = n + 1, n_pad = (int)ks_mma_limb_rows(n);
     dim3 grid((K + 31) / 32, (n_pad / 8 + 31) / 32), block(32, 8);
     ksk_limb_transpose_kernel<<<grid, block, 0, st>>>(ksk, out, K, row, n_pad);
+}
+
+void launch_ks_decompose(const uint64_t* in_big, int8_t* digits, int count, int rows_pad, int big_dim, int base_log, int level,
+                         cudaStream_t st) {
+    ks_decompose_kernel<<<592, 256, 0, st>>>(in_big, digits, count, rows_pad, big_dim, base_log, level);
 }
 
 void launch_keyswitch_mma(const uint8_t* limbs, int8_t* digits, const uint64_t* in_big, uint64_t* out_small, int count, int big_dim,

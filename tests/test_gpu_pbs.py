@@ -39,9 +39,9 @@ def test_keyswitch_bit_exact(gpu_ctx, oracle_keys, rng, preset, count):
     din.free(); dout.free()
 
 
-@pytest.mark.parametrize("variant", ["simt", "mma"])
+@pytest.mark.parametrize("variant", ["simt", "mma", "umma"])
 def test_keyswitch_variants_bit_exact(oracle_keys, rng, variant, monkeypatch):
-    """both keyswitch kernels (CUDA-core and int8 tensor-core limb GEMM) against the oracle, ragged counts."""
+    """the three keyswitch kernels (CUDA cores, mma.sync int8 limb GEMM, tcgen05 int8 limb GEMM) against the oracle, ragged counts."""
     import fhe_sign_b200 as fsb
     from fhe_sign_b200.capi import LWE_BIG, LWE_SMALL
     monkeypatch.setenv("FSC_KS_VARIANT", variant)

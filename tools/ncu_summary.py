@@ -27,6 +27,8 @@ KEYS = [
     "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
     "smsp__average_warp_latency_per_inst_issued.ratio",
     "sm__ops_path_tensor_op_imma_src_int8.avg.pct_of_peak_sustained_elapsed",
+    "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
     "sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_elapsed",
 ]
 
