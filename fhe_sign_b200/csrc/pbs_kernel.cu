@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(64, 4) pbs_pair_kernel(const cplx* __restrict_
 //                s2tab [16][32] cplx (per-lane pass-2 constants) | full[NCH], empty[NCH] mbarriers
 // ---------------------------------------------------------------------------------------
 
-template <typename AccT, int CTS, int NCH, bool XH, bool HS>
+template <typename AccT, int CTS, int NCH, bool XH, bool HS, bool TX>
 __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                                      int n, int base_log, const uint64_t* __restrict__ luts,
                                                                      const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
@@ -249,6 +249,15 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
     if (threadIdx.x == 0) {
         for (int s = 0; s < NCH; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 2 * CTS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t tmem_base = 0;
+    if (TX) {      // 256 TMEM columns: [0, 128) spectra of the p = 0 warps, [128, 256) of the p = 1 warps, one lane quarter per ciphertext
+        uint32_t* slot = reinterpret_cast<uint32_t*>(empty + NCH);
+        if (warp == 0) tmem_alloc_256(slot);
+        tmem_fence_before();
+        __syncthreads();
+        tmem_fence_after();
+        tmem_base = *slot;
     }
     __syncthreads();
 
@@ -272,7 +281,9 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
     }
 
     // ---- consumers: warp (ct, p) owns polynomial p of ciphertext ct ----
-    const int ctl = warp >> 1, p = warp & 1;
+    // TX: the two warps of a ciphertext are w and w + 4, which share a TMEM lane quarter (and an SM sub-partition)
+    static_assert(!TX || (HS && CTS == 4), "the TMEM exchange pairs warps w and w + 4 of a 4-ciphertext CTA");
+    const int ctl = TX ? (warp & 3) : (warp >> 1), p = TX ? (warp >> 2) : (warp & 1);
     const int c_raw = blockIdx.x * CTS + ctl;
     const bool live = c_raw < count;
     const int c = live ? c_raw : count - 1;            // padding warps shadow the last ciphertext, never store
@@ -332,6 +343,75 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
         } else if (XH) warp_fft_fwd_h(lane, reinterpret_cast<double*>(xbuf), c2s, X);
         else warp_fft_fwd_c(lane, xbuf, c2s, X);
 
+        if constexpr (TX) {
+            // Product with the partner's spectrum handed over through tensor memory: 32 slots at once, no shared-memory
+            // traffic for the exchange, one pair barrier for the hand-over and one before the buffer is reused.
+            if (hs_producer) {
+                while (hprod.next_h < 2 * (i + 1) && hprod.next_h < 2 * n) hprod.poll(lane, bsk_f, ring, full, empty, 2 * n);
+            }
+            const uint32_t t_own = tmem_base + ((uint32_t)(ctl * 32) << 16) + (uint32_t)(p * 128);
+            const uint32_t t_oth = tmem_base + ((uint32_t)(ctl * 32) << 16) + (uint32_t)((1 - p) * 128);
+            pair_barrier(1 + ctl);                           // the partner has read the spectrum of the previous step
+            tmem_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                cplx v4[4];
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) v4[rr] = X[k * 4 + rr];
+                tmem_st4(t_own + 16 * k, v4);
+            }
+            tmem_wait_st();
+            tmem_fence_before();
+            const int st0 = hs_stage;
+            mbar_wait(full + hs_stage, hs_phase);
+            if (++hs_stage == NCH) { hs_stage = 0; hs_phase ^= 1; }
+            const int st1 = hs_stage;
+            mbar_wait(full + hs_stage, hs_phase);
+            if (++hs_stage == NCH) { hs_stage = 0; hs_phase ^= 1; }
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {                   // own-spectrum products: hide the wait for the partner
+                const cplx* g = ring + (size_t)(r < 16 ? st0 : st1) * kHalfCplx + lane;
+                const cplx gw = g[((r & 15) * 4 + g_own) * 32];
+                const cplx x = X[r];
+                X[r].x = x.x * gw.x - x.y * gw.y;
+                X[r].y = x.x * gw.y + x.y * gw.x;
+            }
+            pair_barrier(1 + ctl);                           // the partner's spectrum is in tensor memory
+            tmem_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                cplx o4[4];
+                tmem_ld4(t_oth + 16 * k, o4);
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int r = k * 4 + rr;
+                    const cplx* g = ring + (size_t)(r < 16 ? st0 : st1) * kHalfCplx + lane;
+                    const cplx go = g[((r & 15) * 4 + g_oth) * 32];
+                    X[r].x += o4[rr].x * go.x - o4[rr].y * go.y;
+                    X[r].y += o4[rr].x * go.y + o4[rr].y * go.x;
+                }
+            }
+            tmem_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(empty + st0); mbar_arrive(empty + st1); }
+            pass32_inv_gs(X, c2s);
+            {
+                double* xb = reinterpret_cast<double*>(xbuf);
+                xpose_store_inv_h(lane, xb, X, 0);
+                __syncwarp();
+                xpose_load_inv_h(lane, xb, X, 0);
+                __syncwarp();
+                xpose_store_inv_h(lane, xb, X, 1);
+                __syncwarp();
+                xpose_load_inv_h(lane, xb, X, 1);
+                __syncwarp();
+            }
+            dft32_inv(X, S1PlainDev());
+            cmux_tail<AccT>(lane, acc, X);
+            __syncwarp();
+            if (hs_producer) hprod.poll(lane, bsk_f, ring, full, empty, 2 * n);
+            continue;
+        }
         if constexpr (HS) {
             // Half-step product (same order as pbs_stream_kernel): the own-spectrum products run between the exchange
             // store and the pair barrier, so the wait for the partner hides behind 64 FMAs; one barrier wait and one
@@ -436,6 +516,11 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
         const pair_t<AccT>* mask = acc_all + (size_t)(ctl * 2) * 1024;
         for (int j = (p * 32 + lane); j <= kN; j += 64) out[j] = extract_word<AccT>(mask, mask + 1024, j);
     }
+    if (TX) {
+        tmem_fence_before();
+        __syncthreads();
+        if (warp == 0) { tmem_fence_after(); tmem_dealloc_256(tmem_base); }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -491,18 +576,18 @@ static void launch_pbs_pair_t(const void* bsk_f, const uint64_t* in_small, int n
                                                     lut_idx, out_big, out_idx, count);
 }
 
-template <typename AccT, int CTS, int NCH, bool XH, bool HS>
+template <typename AccT, int CTS, int NCH, bool XH, bool HS, bool TX = false>
 static void launch_pbs_ring_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
                               const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     const size_t smem = (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>) + (size_t)CTS * 2 * (XH ? 512 : 1024) * sizeof(cplx) +
-                        (size_t)NCH * (HS ? kHalfCplx : kChunkCplx) * sizeof(cplx) + 16 * 32 * sizeof(cplx) + 2 * NCH * sizeof(uint64_t);
+                        (size_t)NCH * (HS ? kHalfCplx : kChunkCplx) * sizeof(cplx) + 16 * 32 * sizeof(cplx) + 2 * NCH * sizeof(uint64_t) + 16;
     static bool configured = false;
     if (!configured) {
-        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_ring_kernel<AccT, CTS, NCH, XH, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_ring_kernel<AccT, CTS, NCH, XH, HS, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     const int grid = (count + CTS - 1) / CTS;
-    pbs_ring_kernel<AccT, CTS, NCH, XH, HS><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log,
+    pbs_ring_kernel<AccT, CTS, NCH, XH, HS, TX><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log,
                                                                         luts, lut_idx, out_big, out_idx, count);
 }
 
@@ -537,7 +622,8 @@ void launch_pbs(int variant, int acc_bits, const void* bsk_f, const uint64_t* in
     } else if (acc_bits == 32) {
         if (count <= sm_count) FSC_RING(uint32_t, 1, 3);
         else if (count <= 2 * sm_count) FSC_RING(uint32_t, 2, 3);
-        else FSC_RING(uint32_t, 4, 2);
+        else if (getenv("FSC_RING_NO_TMEM")) FSC_RING(uint32_t, 4, 2);      // partner exchange through shared memory (comparison)
+        else launch_pbs_ring_t<uint32_t, 4, 2, true, true, true>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
     } else {
         // 64-bit accumulator: the chunked ring (8 KB chunks, blocking producer) measures faster than the half-step ring
         // here (47.0 k against 42.1 k PBS/s at 4096 blocks)

@@ -104,4 +104,44 @@ struct HalfProducer {
     }
 };
 
+// ---- tensor memory (TMEM) as a lane-aligned exchange buffer ----------------------------------------------------
+// Warps w and w + 4 of a CTA address the same 32 TMEM lanes (w % 4); thread t of either warp reaches lane t of that
+// quarter.  What one of them stores with tcgen05.st the other reads back with tcgen05.ld at the same (lane, column):
+// a register-to-register hand-over between the two warps that does not touch the shared-memory pipe.
+__device__ __forceinline__ void tmem_alloc_256(uint32_t* slot_in_smem) {      // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(slot_in_smem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_256(uint32_t taddr) {            // one full warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// four complex doubles (16 x 32 bit) of the calling thread's lane <-> 16 consecutive columns
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const cplx (&v)[4]) {
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        w[4 * i + 0] = (uint32_t)__double2loint(v[i].x); w[4 * i + 1] = (uint32_t)__double2hiint(v[i].x);
+        w[4 * i + 2] = (uint32_t)__double2loint(v[i].y); w[4 * i + 3] = (uint32_t)__double2hiint(v[i].y);
+    }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]),
+                 "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, cplx (&v)[4]) {      // tmem_wait_ld() before the values are used
+    uint32_t w[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
+                   "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]) : "r"(taddr) : "memory");
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[i].x = __hiloint2double((int)w[4 * i + 1], (int)w[4 * i + 0]);
+        v[i].y = __hiloint2double((int)w[4 * i + 3], (int)w[4 * i + 2]);
+    }
+}
+
 }  // namespace fsc
