@@ -26,9 +26,18 @@
 //
 // Everything is __host__ __device__ with `lane` as an argument: tests/emu/pbs_emu2.cpp runs the same code on the CPU.
 #pragma once
+#include <type_traits>
+#include <utility>
 #include "pbs_core.cuh"
 
 namespace fsc {
+
+// constant providers may fetch a whole butterfly level at once (begin_level); the others are asked node by node
+template <class T, class = void> struct has_begin_level : std::false_type {};
+template <class T> struct has_begin_level<T, std::void_t<decltype(std::declval<const T&>().begin_level(0))>> : std::true_type {};
+template <class SP> FSC_HD void provider_begin_level(const SP& sp, int L) {
+    if constexpr (has_begin_level<SP>::value) sp.begin_level(L);
+}
 
 // ---- constant tables --------------------------------------------------------------------
 // entry ci of the table of a pass with root parameter g: ci = 0 -> (re, im); ci >= 1 -> (cos, tan)
@@ -60,6 +69,7 @@ FSC_HD constexpr int freq_pos(int k1) {            // k1 -> position
 template <class SP>
 FSC_HD void pass32(cplx (&v)[32], const SP& sp) {
     {   // level 1: (re, im) constant
+        provider_begin_level(sp, 1);
         const cplx s = sp.get(0);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -73,6 +83,7 @@ FSC_HD void pass32(cplx (&v)[32], const SP& sp) {
 #pragma unroll
     for (int L = 2; L <= 5; ++L) {
         const int half = 16 >> (L - 1);
+        provider_begin_level(sp, L);
 #pragma unroll
         for (int m = 0; m < (1 << (L - 1)); ++m) {
             const int base = m * 2 * half;
@@ -103,6 +114,7 @@ FSC_HD void pass32_inv_gs(cplx (&v)[32], const SP& sp) {
 #pragma unroll
     for (int L = 5; L >= 1; --L) {
         const int half = 16 >> (L - 1);
+        provider_begin_level(sp, L);
 #pragma unroll
         for (int m = 0; m < (1 << (L - 1)); ++m) {
             const int base = m * 2 * half;

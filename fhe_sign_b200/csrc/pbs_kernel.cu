@@ -22,6 +22,13 @@
 #include "fsc_internal.h"
 #include "tma_ring.cuh"
 
+#ifndef FSC_TX_CONSTS
+#define FSC_TX_CONSTS 0      // per-lane pass-2 constants from tensor memory: measured slower (a wait per butterfly level)
+#endif
+#ifndef FSC_TX_ACC
+#define FSC_TX_ACC 1
+#endif
+
 namespace fsc {
 
 __constant__ cplx c_p1[16];            // forward pass 1 / inverse pass 1 node constants (re, im), g = 32 (pbs_core.cuh lane_consts)
@@ -251,9 +258,12 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     uint32_t tmem_base = 0;
-    if (TX) {      // 256 TMEM columns: [0, 128) spectra of the p = 0 warps, [128, 256) of the p = 1 warps, one lane quarter per ciphertext
+    // TX, tensor memory columns of a ciphertext's lane quarter: [0, 256) spectra of warp p = 0 | 1 (exchange),
+    // [256, 320) per-lane pass-2 constants, [320, 448) own-index accumulator pairs of warp p = 0 | 1
+    constexpr int kTmemCols = 512, kTmConsts = 256, kTmAcc = 320;
+    if (TX) {
         uint32_t* slot = reinterpret_cast<uint32_t*>(empty + NCH);
-        if (warp == 0) tmem_alloc_256(slot);
+        if (warp == 0) tmem_alloc<kTmemCols>(slot);
         tmem_fence_before();
         __syncthreads();
         tmem_fence_after();
@@ -282,7 +292,7 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
 
     // ---- consumers: warp (ct, p) owns polynomial p of ciphertext ct ----
     // TX: the two warps of a ciphertext are w and w + 4, which share a TMEM lane quarter (and an SM sub-partition)
-    static_assert(!TX || (HS && CTS == 4), "the TMEM exchange pairs warps w and w + 4 of a 4-ciphertext CTA");
+    static_assert(!TX || (HS && CTS == 4 && sizeof(AccT) == 4), "the TMEM exchange pairs warps w and w + 4 of a 4-ciphertext CTA (32-bit accumulator)");
     const int ctl = TX ? (warp & 3) : (warp >> 1), p = TX ? (warp >> 2) : (warp & 1);
     const int c_raw = blockIdx.x * CTS + ctl;
     const bool live = c_raw < count;
@@ -306,7 +316,39 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
     }
     __syncthreads();
     const SmemLaneConsts c2s{s2tab + lane};
-    {
+    const uint32_t t_quarter = tmem_base + ((uint32_t)(ctl * 32) << 16);
+    const TmemLaneConsts c2t{t_quarter + kTmConsts, {}, 0};
+    if (TX && p == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            cplx v4[4];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) v4[rr] = s2tab[(k * 4 + rr) * 32 + lane];
+            tmem_st4(t_quarter + kTmConsts + 16 * k, v4);
+        }
+        tmem_wait_st();
+    }
+    const uint32_t t_acc = t_quarter + kTmAcc + (uint32_t)(p * 64);      // own-index accumulator pairs (TX)
+    if (TX) {
+        const int b = modswitch(ct[n]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t w[16];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = lane + 32 * (8 * k + u);
+                pair_t<AccT> z; z.x = 0; z.y = 0;
+                if (p) z = lut_pair<AccT>(lut, idx, b);
+                acc[idx] = z;
+                w[2 * u] = (uint32_t)z.x; w[2 * u + 1] = (uint32_t)z.y;
+            }
+            tmem_stw16(t_acc + 16 * k, w);
+        }
+        tmem_wait_st();
+        tmem_fence_before();
+        pair_barrier(1 + ctl);      // the constants staged by the p = 0 warp are visible to its partner
+        tmem_fence_after();
+    } else {
         const int b = modswitch(ct[n]);
 #pragma unroll 4
         for (int j2 = 0; j2 < 32; ++j2) {
@@ -327,7 +369,24 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
         // a == 0 is not skipped: the ring is shared by all ciphertexts of the CTA; the step is an exact no-op
 
         cplx X[32];
-        cmux_head<AccT>(lane, acc, a, base_log, X);      // (the ALU/FMA-split head of pbs_head.cuh measures 3 % slower here)
+        if constexpr (TX && FSC_TX_ACC) {
+            // head with the own-index pairs read from tensor memory: one shared-memory load per element (the rotated pair)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t w[16];
+                tmem_ldw16(t_acc + 16 * k, w);
+                tmem_wait_ld();
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j2 = 8 * k + u;
+                    const pair_t<AccT> R = rotated_pair<AccT>(acc, lane + 32 * j2, a);
+                    X[j2].x = decomp_digit<AccT>((AccT)(R.x - (AccT)w[2 * u]), base_log);
+                    X[j2].y = decomp_digit<AccT>((AccT)(R.y - (AccT)w[2 * u + 1]), base_log);
+                }
+            }
+        } else {
+            cmux_head<AccT>(lane, acc, a, base_log, X);      // (the ALU/FMA-split head of pbs_head.cuh measures 3 % slower here)
+        }
         if (HS) {      // forward passes in the 6-FMA tangent form (pass32), same node constants as dft32_fwd
             double* xb = reinterpret_cast<double*>(xbuf);
             pass32(X, WT0Dev());
@@ -339,7 +398,8 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
             __syncwarp();
             xpose_load_fwd_h(lane, xb, X, 1);
             __syncwarp();
-            pass32(X, c2s);
+            if constexpr (TX && FSC_TX_CONSTS) pass32(X, c2t);
+            else pass32(X, c2s);
         } else if (XH) warp_fft_fwd_h(lane, reinterpret_cast<double*>(xbuf), c2s, X);
         else warp_fft_fwd_c(lane, xbuf, c2s, X);
 
@@ -394,7 +454,8 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
             tmem_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(empty + st0); mbar_arrive(empty + st1); }
-            pass32_inv_gs(X, c2s);
+            if constexpr (FSC_TX_CONSTS) pass32_inv_gs(X, c2t);
+            else pass32_inv_gs(X, c2s);
             {
                 double* xb = reinterpret_cast<double*>(xbuf);
                 xpose_store_inv_h(lane, xb, X, 0);
@@ -407,7 +468,26 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
                 __syncwarp();
             }
             dft32_inv(X, S1PlainDev());
-            cmux_tail<AccT>(lane, acc, X);
+            // tail: own-index pairs from tensor memory, updated values to shared memory (for the rotated reads) and back
+            if constexpr (!FSC_TX_ACC) cmux_tail<AccT>(lane, acc, X);
+            else
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t w[16];
+                tmem_ldw16(t_acc + 16 * k, w);
+                tmem_wait_ld();
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j2 = 8 * k + u;
+                    pair_t<AccT> O;
+                    O.x = (AccT)((AccT)w[2 * u] + to_acc<AccT>(X[j2].x));
+                    O.y = (AccT)((AccT)w[2 * u + 1] + to_acc<AccT>(X[j2].y));
+                    acc[lane + 32 * j2] = O;
+                    w[2 * u] = (uint32_t)O.x; w[2 * u + 1] = (uint32_t)O.y;
+                }
+                tmem_stw16(t_acc + 16 * k, w);
+            }
+            tmem_wait_st();
             __syncwarp();
             if (hs_producer) hprod.poll(lane, bsk_f, ring, full, empty, 2 * n);
             continue;
@@ -519,7 +599,7 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
     if (TX) {
         tmem_fence_before();
         __syncthreads();
-        if (warp == 0) { tmem_fence_after(); tmem_dealloc_256(tmem_base); }
+        if (warp == 0) { tmem_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
     }
 }
 

@@ -108,12 +108,14 @@ struct HalfProducer {
 // Warps w and w + 4 of a CTA address the same 32 TMEM lanes (w % 4); thread t of either warp reaches lane t of that
 // quarter.  What one of them stores with tcgen05.st the other reads back with tcgen05.ld at the same (lane, column):
 // a register-to-register hand-over between the two warps that does not touch the shared-memory pipe.
-__device__ __forceinline__ void tmem_alloc_256(uint32_t* slot_in_smem) {      // one full warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(slot_in_smem)) : "memory");
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem) {          // one full warp; COLS: power of two >= 32
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "n"(COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_dealloc_256(uint32_t taddr) {            // one full warp
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(taddr) : "memory");
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {                // one full warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
 __device__ __forceinline__ void tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -131,6 +133,68 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const cplx (&v)[4]) {
                  ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]),
                  "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]) : "memory");
 }
+// raw 32-bit columns of the calling thread's lane
+__device__ __forceinline__ void tmem_ldw4(uint32_t taddr, uint32_t (&w)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ldw8(uint32_t taddr, uint32_t (&w)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ldw16(uint32_t taddr, uint32_t (&w)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
+                   "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_stw16(uint32_t taddr, const uint32_t (&w)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]),
+                 "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]) : "memory");
+}
+__device__ __forceinline__ cplx cplx_from_words(uint32_t xl, uint32_t xh, uint32_t yl, uint32_t yh) {
+    cplx c;
+    c.x = __hiloint2double((int)xh, (int)xl);
+    c.y = __hiloint2double((int)yh, (int)yl);
+    return c;
+}
+
+// Per-lane node constants of a 32-point pass kept in tensor memory (16 complex = 64 columns of the lane): pass32 /
+// pass32_inv_gs call begin_level(L) once per butterfly level and get(ci) per node; the level's 1, 1, 2, 4 or 8 constants
+// come in with one tcgen05.ld instead of that many shared-memory loads.
+struct TmemLaneConsts {
+    uint32_t taddr;
+    mutable cplx c[8];
+    mutable int ci0;
+    __device__ __forceinline__ void begin_level(int L) const {
+        ci0 = (L == 1) ? 0 : (1 << (L - 2));
+        const int nconst = (L <= 2) ? 1 : (1 << (L - 2));
+        if (nconst == 1) {
+            uint32_t w[4];
+            tmem_ldw4(taddr + 4 * ci0, w);
+            tmem_wait_ld();
+            c[0] = cplx_from_words(w[0], w[1], w[2], w[3]);
+        } else if (nconst == 2) {
+            uint32_t w[8];
+            tmem_ldw8(taddr + 4 * ci0, w);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 2; ++i) c[i] = cplx_from_words(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (h * 4 < nconst) {
+                    uint32_t w[16];
+                    tmem_ldw16(taddr + 4 * ci0 + 16 * h, w);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) c[h * 4 + i] = cplx_from_words(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ cplx get(int ci) const { return c[ci - ci0]; }
+};
+
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, cplx (&v)[4]) {      // tmem_wait_ld() before the values are used
     uint32_t w[16];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
