@@ -270,6 +270,265 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_stream_kernel(const cplx* __r
 }
 
 // ---------------------------------------------------------------------------------------
+// Wide-batch variant with tensor memory (32-bit accumulator, 4 ciphertexts per CTA).  The two warps of a ciphertext
+// are w and w + 4: they share a TMEM lane quarter, so everything that one thread hands to "the same lane" — of its
+// partner warp or of itself later — goes through tcgen05.st / tcgen05.ld instead of the shared-memory pipe:
+//   columns [0, 256)    spectra for the partner exchange (warp p writes [128 p, 128 p + 128), position order)
+//   columns [256, 384)  own-index accumulator pairs of warp p at [256 + 64 p, ...), in the tail's position order
+//   columns [384, 512)  the lane's 32 twist constants (written once by the p = 0 warp)
+// Shared memory keeps what crosses lanes: the accumulator copy for the rotated reads, the transposes, the key ring,
+// the per-lane pass tables.  One pair barrier hands the spectra over, one guards their reuse.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
+                                                                 int n, int base_log, const uint64_t* __restrict__ luts,
+                                                                 const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
+                                                                 const int32_t* __restrict__ out_idx, int count,
+                                                                 const cplx* __restrict__ tabs_g) {
+    typedef uint32_t AccT;
+    constexpr int CTS = 4, NH = 2;
+    constexpr int kTmAcc = 256, kTmTwist = 384, kTmemCols = 512;
+    constexpr int kTabNoTwist = kTabTwist;               // the twist table lives in tensor memory
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    pair_t<AccT>* acc_all = reinterpret_cast<pair_t<AccT>*>(smem_raw);
+    double* xbuf_all = reinterpret_cast<double*>(smem_raw + (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>));
+    cplx* ring = reinterpret_cast<cplx*>(xbuf_all + (size_t)CTS * 2 * kXBufDoubles);
+    cplx* tabs = ring + (size_t)NH * kHalfCplx;
+    uint64_t* full = reinterpret_cast<uint64_t*>(tabs + kTabNoTwist);
+    uint64_t* empty = full + NH;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty + NH);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NH; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 2 * CTS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int t = threadIdx.x; t < kTabNoTwist; t += CTS * 64) {
+        const double2 d = __ldg(reinterpret_cast<const double2*>(tabs_g + t));
+        tabs[t].x = d.x; tabs[t].y = d.y;
+    }
+    if (warp == 0) tmem_alloc<kTmemCols>(tmem_slot);
+    tmem_fence_before();
+    __syncthreads();
+    tmem_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_halves = 2 * n;
+    const bool producer = warp == 0;                   // warp-uniform
+    HalfProducer<NH> prod;
+    prod.init();
+    if (producer) prod.poll(lane, bsk_f, ring, full, empty, total_halves);
+
+    const int ctl = warp & 3, p = warp >> 2;
+    const int c_raw = blockIdx.x * CTS + ctl;
+    const bool live = c_raw < count;
+    const int c = live ? c_raw : count - 1;            // padding warps shadow the last ciphertext, never store
+    pair_t<AccT>* acc = acc_all + (size_t)(ctl * 2 + p) * 1024;
+    double* xb = xbuf_all + (size_t)(ctl * 2 + p) * kXBufDoubles;
+    const uint64_t* ct = in_small + (size_t)c * (n + 1);
+    const uint64_t* lut = luts + (size_t)(lut_idx ? lut_idx[c] : 0) * kN;
+    const uint32_t t_quarter = tmem_base + ((uint32_t)(ctl * 32) << 16);
+    const uint32_t t_own = t_quarter + (uint32_t)(p * 128), t_oth = t_quarter + (uint32_t)((1 - p) * 128);
+    const uint32_t t_acc = t_quarter + kTmAcc + (uint32_t)(p * 64), t_tw = t_quarter + kTmTwist;
+
+    if (p == 0) {      // the lane's twist constants, position order: 8 x 16 columns
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            cplx v4[4];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const double2 d = __ldg(reinterpret_cast<const double2*>(tabs_g + kTabTwist + (k * 4 + rr) * 32 + lane));
+                v4[rr].x = d.x; v4[rr].y = d.y;
+            }
+            tmem_st4(t_tw + 16 * k, v4);
+        }
+    }
+    {   // accumulator <- (0, X^{-b} LUT): shared memory by index, tensor memory in the tail's position order
+        const int b = modswitch(ct[n]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t w[16];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = lane + 32 * tail_j2(8 * k + u);
+                pair_t<AccT> z; z.x = 0; z.y = 0;
+                if (p) z = lut_pair<AccT>(lut, idx, b);
+                acc[idx] = z;
+                w[2 * u] = z.x; w[2 * u + 1] = z.y;
+            }
+            tmem_stw16(t_acc + 16 * k, w);
+        }
+    }
+    tmem_wait_st();
+    tmem_fence_before();
+    pair_barrier(1 + ctl);      // the twist constants staged by the p = 0 warp are visible to its partner
+    tmem_fence_after();
+
+    const int g_own = 3 * p, g_oth = 2 - p;
+    const int row_inv = (32 - lane) & 31;
+    int a_chunk = 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    cplx X[32];
+    for (int i = 0; i < n; ++i) {
+        if ((i & 31) == 0) a_chunk = (i + lane < n) ? modswitch(ct[i + lane]) : 0;
+        const int a = __shfl_sync(0xffffffffu, a_chunk, i & 31);
+
+        auto do_head = [&]() {
+            // stream_head_u32 with the own-index pairs from tensor memory; elements visited in the tail's position order
+            const int sh = 32 - base_log;
+            const int half = 1 << (sh - 1);
+            const int base = (lane - a) & 4095;
+            const int q0 = base >> 10, q1 = (q0 + 1) & 3;
+            const int swA = q0 & 1;
+            const int sxA = 1 - (q0 & 2), syA = 1 - ((q0 ^ (q0 << 1)) & 2);
+            const int sxB = 1 - (q1 & 2), syB = 1 - ((q1 ^ (q1 << 1)) & 2);
+            const int dsx = sxB - sxA, dsy = syB - syA;
+            unsigned b8 = (unsigned)(base & 1023) << 3;
+            const char* pb = reinterpret_cast<const char*>(acc);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t w[16];
+                tmem_ldw16(t_acc + 16 * k, w);
+                tmem_wait_ld();
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j2 = tail_j2(8 * k + u);
+                    if ((u & 3) == 0) asm volatile("" : "+r"(b8));
+                    const unsigned uu = b8 + 256u * j2;
+                    const int cc = (int)(uu >> 13);
+                    const uint2 P = *reinterpret_cast<const uint2*>(pb + (uu & 8191u));
+                    const int sw = swA ^ cc;
+                    const int sx = imad(cc, dsx, sxA), sy = imad(cc, dsy, syA);
+                    const int e = (int)(P.y - P.x);
+                    const int px = imad(sw, e, (int)P.x);
+                    const int py = (int)(P.x + P.y) - px;
+                    const int dx = imad(px, sx, half - (int)w[2 * u]);
+                    const int dy = imad(py, sy, half - (int)w[2 * u + 1]);
+                    X[j2].x = __hiloint2double(0x43300000, (dx >> sh) ^ (int)0x80000000) - 4503601774854144.0;
+                    X[j2].y = __hiloint2double(0x43300000, (dy >> sh) ^ (int)0x80000000) - 4503601774854144.0;
+                }
+            }
+        };
+        auto xp_out = [&]() {
+            xp_store(lane, xb, X, 0);
+            __syncwarp();
+        };
+        auto xp_in = [&](int row) {
+            xp_load(row, xb, X, 0);
+            __syncwarp();
+            xp_store(lane, xb, X, 1);
+            __syncwarp();
+            xp_load(row, xb, X, 1);
+            __syncwarp();
+        };
+        auto do_mac = [&]() {
+            if (producer) {      // both halves of this step requested before anyone sleeps on them (see pbs_stream_kernel)
+                while (prod.next_h < 2 * (i + 1) && prod.next_h < total_halves)
+                    prod.poll(lane, bsk_f, ring, full, empty, total_halves);
+            }
+            pair_barrier(1 + ctl);                           // the partner has read the spectrum of the previous step
+            tmem_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {                    // position order: the partner reads 4 consecutive positions per load
+                cplx v4[4];
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) v4[rr] = X[brev5(freq_at(4 * k + rr))];
+                tmem_st4(t_own + 16 * k, v4);
+            }
+            tmem_wait_st();
+            tmem_fence_before();
+            const int st0 = stage;
+            mbar_wait(full + stage, phase);
+            if (++stage == NH) { stage = 0; phase ^= 1; }
+            const int st1 = stage;
+            mbar_wait(full + stage, phase);
+            if (++stage == NH) { stage = 0; phase ^= 1; }
+            const cplx* g0 = ring + (size_t)st0 * kHalfCplx + lane;
+            const cplx* g1 = ring + (size_t)st1 * kHalfCplx + lane;
+            auto own = [&](auto kc) {
+                constexpr int K = decltype(kc)::value;       // chunk of 4 positions; K < 4: first key half
+                const cplx* g = (K < 4 ? g0 : g1);
+                cplx gw[4];
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) gw[rr] = g[(((K & 3) * 4 + rr) * 4 + g_own) * 32];
+                mac_own<K * 4>(X, gw);
+            };
+            own(std::integral_constant<int, 0>{}); own(std::integral_constant<int, 1>{});
+            own(std::integral_constant<int, 2>{}); own(std::integral_constant<int, 3>{});
+            own(std::integral_constant<int, 4>{}); own(std::integral_constant<int, 5>{});
+            own(std::integral_constant<int, 6>{}); own(std::integral_constant<int, 7>{});
+            pair_barrier(1 + ctl);                           // the partner's spectrum is in tensor memory
+            tmem_fence_after();
+            auto oth = [&](auto kc) {
+                constexpr int K = decltype(kc)::value;
+                const cplx* g = (K < 4 ? g0 : g1);
+                cplx o[4], go[4];
+                tmem_ld4(t_oth + 16 * K, o);
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) go[rr] = g[(((K & 3) * 4 + rr) * 4 + g_oth) * 32];
+                mac_oth<K * 4>(X, o, go);
+            };
+            oth(std::integral_constant<int, 0>{}); oth(std::integral_constant<int, 1>{});
+            oth(std::integral_constant<int, 2>{}); oth(std::integral_constant<int, 3>{});
+            oth(std::integral_constant<int, 4>{}); oth(std::integral_constant<int, 5>{});
+            oth(std::integral_constant<int, 6>{}); oth(std::integral_constant<int, 7>{});
+            tmem_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(empty + st0); mbar_arrive(empty + st1); }
+        };
+        auto do_tail = [&]() {
+            // twist constants and own-index pairs from tensor memory; results to shared memory (rotated reads) and back
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t tw[32], w[16];
+                tmem_ldw32(t_tw + 32 * k, tw);
+                tmem_ldw16(t_acc + 16 * k, w);
+                tmem_wait_ld();
+                double re[8], im[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const cplx t = cplx_from_words(tw[4 * u], tw[4 * u + 1], tw[4 * u + 2], tw[4 * u + 3]);
+                    const cplx x = X[8 * k + u];
+                    re[u] = fma(-x.y, t.y, x.x * t.x);
+                    im[u] = fma(x.y, t.x, x.x * t.y);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    pair_t<AccT> O;
+                    O.x = w[2 * u] + to_acc_scaled<AccT>(re[u]);
+                    O.y = w[2 * u + 1] + to_acc_scaled<AccT>(im[u]);
+                    acc[lane + 32 * tail_j2(8 * k + u)] = O;
+                    w[2 * u] = O.x; w[2 * u + 1] = O.y;
+                }
+                tmem_stw16(t_acc + 16 * k, w);
+            }
+            tmem_wait_st();
+            __syncwarp();
+        };
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            if (q == 0) do_head();
+            else if (q & 1) xp_in(q == 1 ? lane : row_inv);
+            pass32(X, pass_table(tabs, q, lane));
+            if (!(q & 1)) xp_out();
+            else if (q == 1) do_mac();
+            else do_tail();
+        }
+        if (producer) prod.poll(lane, bsk_f, ring, full, empty, total_halves);
+    }
+    pair_barrier(1 + ctl);
+
+    if (live) {
+        uint64_t* out = out_big + (size_t)(out_idx ? out_idx[c] : c) * (kN + 1);
+        const pair_t<AccT>* mask = acc_all + (size_t)(ctl * 2) * 1024;
+        for (int j = (p * 32 + lane); j <= kN; j += 64) out[j] = extract_word<AccT>(mask, mask + 1024, j);
+    }
+    tmem_fence_before();
+    __syncthreads();
+    if (warp == 0) { tmem_fence_after(); tmem_dealloc<kTmemCols>(tmem_base); }
+}
+
+// ---------------------------------------------------------------------------------------
 // Test hook: c = a (torus) * b (small integers), negacyclic, through the stream FFT.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) negacyclic_mul_stream_kernel(const uint64_t* __restrict__ a, const int64_t* __restrict__ b,
@@ -337,6 +596,19 @@ static void launch_pbs_stream_t(const void* bsk_f, const uint64_t* in_small, int
                                                                           lut_idx, out_big, out_idx, count, stream_tables<AccT>());
 }
 
+static void launch_pbs_stream_tx(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
+                                 const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
+    const size_t smem = (size_t)4 * 2 * 1024 * sizeof(pair_t<uint32_t>) + (size_t)4 * 2 * kXBufDoubles * sizeof(double) +
+                        (size_t)2 * kHalfCplx * sizeof(cplx) + (size_t)kTabTwist * sizeof(cplx) + 2 * 2 * sizeof(uint64_t) + 16;
+    static bool configured = false;
+    if (!configured) {
+        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_stream_tx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    pbs_stream_tx_kernel<<<(count + 3) / 4, 256, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts, lut_idx,
+                                                             out_big, out_idx, count, stream_tables<uint32_t>());
+}
+
 // Configuration by batch width: wide levels pack 4 (u32 accumulator) or 3 (u64) ciphertexts per CTA so that one key
 // chunk feeds them all; levels of at most one or two ciphertexts per SM use 1 or 2 per CTA (the latency-bound case of
 // the carry-propagation levels: a less contended SM per ciphertext).
@@ -348,7 +620,8 @@ void launch_pbs_stream(int acc_bits, const void* bsk_f, const uint64_t* in_small
     if (acc_bits == 32) {
         if (count <= sm_count) FSC_STREAM(uint32_t, 1, 3);
         else if (count <= 2 * sm_count) FSC_STREAM(uint32_t, 2, 3);
-        else FSC_STREAM(uint32_t, 4, 2);
+        else if (getenv("FSC_STREAM_NO_TMEM")) FSC_STREAM(uint32_t, 4, 2);
+        else launch_pbs_stream_tx(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
     } else {
         // 64-bit accumulator: two ciphertexts per CTA is what fits beside a whole-step ring (the product default for
         // 64-bit accumulators is the ring kernel of pbs_kernel.cu, three per CTA)
