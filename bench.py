@@ -30,7 +30,7 @@ WORKLOAD = "batched PBS microbench: %d LWE blocks, PARAM_MESSAGE_2_CARRY_2 (%s),
 
 
 # DRAM bytes (read + write) of one 4096-block launch, from the ncu --set full captures summarised in profiles/
-NCU_TRAFFIC = {"pbs_ring_kernel": 216.18e6, "pbs_stream_kernel": 263.39e6}      # profiles/r01b_ncu_key_metrics.json
+NCU_TRAFFIC = {"pbs_ring_kernel": 202.69e6, "pbs_stream_kernel": 233.47e6}      # profiles/r01c_ncu_key_metrics.json
 
 
 def flops_per_pbs(n, N=2048, k=1, l=1):

@@ -505,7 +505,11 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
             tmem_wait_st();
             __syncwarp();
         };
+#ifdef FSC_STREAM_TX_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
         for (int q = 0; q < 4; ++q) {
             if (q == 0) do_head();
             else if (q & 1) xp_in(q == 1 ? lane : row_inv);
