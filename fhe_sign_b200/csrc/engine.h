@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <vector>
 #include "fsc_internal.h"
 
 namespace fsc {
@@ -36,6 +37,11 @@ struct Engine {
     void* pinned = nullptr;
     size_t pinned_cap = 0;
     uint64_t launches = 0;
+    // host-buffer entry point: two copy streams so that uploads and downloads overlap the bootstraps of other chunks
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    std::vector<cudaEvent_t> chunk_events;
+    size_t host_chunk_waves = 1;         // chunk = this many waves of the blind-rotation kernel (FSC_HOST_CHUNK_WAVES; 0 = no overlap)
 
     Engine(const fsc_params& prm, int device, uintptr_t ext_stream);
     ~Engine();
@@ -46,6 +52,8 @@ struct Engine {
     void upload_keys(const uint64_t* bsk_std, size_t bsk_words, const uint64_t* ksk_h, size_t ksk_words);
     void ensure_scratch(size_t count);
     void ensure_pinned(size_t bytes);
+    void ensure_copy_streams();
+    cudaEvent_t chunk_event(size_t i);
     const uint32_t* stage_lut_idx(const uint32_t* lut_idx, size_t count, const Luts* luts);
     void keyswitch(const uint64_t* in_big, uint64_t* out_small, size_t count);
     void pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut_idx_dev, uint64_t* out_big, size_t count,

@@ -57,6 +57,25 @@ Engine::Engine(const fsc_params& prm, int device, uintptr_t ext_stream) : p(prm)
     pbs_init_constants();
     const char* kv = getenv("FSC_KS_VARIANT");      // "simt" | "mma" (default)
     ks_variant = (kv && kv[0] == 's') ? 0 : (kv && kv[0] == 'm') ? 1 : 2;      // simt | mma | umma (default)
+    if (const char* hw = getenv("FSC_HOST_CHUNK_WAVES")) host_chunk_waves = (size_t)atoi(hw);      // 0: one chunk, copies not overlapped
+}
+
+void Engine::ensure_copy_streams() {
+    if (copy_in) return;
+    use();
+    FSC_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking));
+    FSC_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking));
+    FSC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    FSC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+}
+
+cudaEvent_t Engine::chunk_event(size_t i) {
+    while (chunk_events.size() <= i) {
+        cudaEvent_t ev = nullptr;
+        FSC_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        chunk_events.push_back(ev);
+    }
+    return chunk_events[i];
 }
 
 Engine::~Engine() {
@@ -73,6 +92,11 @@ Engine::~Engine() {
     if (pinned) cudaFreeHost(pinned);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    for (cudaEvent_t ev : chunk_events) cudaEventDestroy(ev);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (copy_in) { cudaStreamSynchronize(copy_in); cudaStreamDestroy(copy_in); }
+    if (copy_out) { cudaStreamSynchronize(copy_out); cudaStreamDestroy(copy_out); }
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -460,9 +484,38 @@ fsc_status fsc_apply_lut_host(fsc_ctx* ctx, const uint64_t* in_host, const fsc_l
         uint64_t* din = e->scratch_big;
         uint64_t* dout = e->scratch_big + e->scratch_big_cap * words;
         const uint32_t* di = e->stage_lut_idx(lut_idx, count, luts);
-        FSC_CUDA_CHECK(cudaMemcpyAsync(din, in_host, count * words * 8, cudaMemcpyHostToDevice, e->stream));
-        e->ks_pbs(din, luts, di, dout, count);
-        FSC_CUDA_CHECK(cudaMemcpyAsync(out_host, dout, count * words * 8, cudaMemcpyDeviceToHost, e->stream));
+        // Copies overlap the bootstraps: the batch is cut at whole waves of the blind-rotation kernel (4 or 3
+        // ciphertexts per SM), chunk c + 1 uploads and chunk c - 1 downloads on two copy streams while chunk c computes, so only
+        // the first upload and the last download are exposed.
+        const size_t wave = (size_t)e->sm_count * (e->p.acc_bits == 32 ? 4 : 3);
+        const size_t chunk = e->host_chunk_waves ? e->host_chunk_waves * wave : count;
+        if (count <= chunk + wave / 2) {
+            FSC_CUDA_CHECK(cudaMemcpyAsync(din, in_host, count * words * 8, cudaMemcpyHostToDevice, e->stream));
+            e->ks_pbs(din, luts, di, dout, count);
+            FSC_CUDA_CHECK(cudaMemcpyAsync(out_host, dout, count * words * 8, cudaMemcpyDeviceToHost, e->stream));
+        } else {
+            e->ensure_copy_streams();
+            e->ensure_scratch(count);
+            const size_t nsmall = (size_t)e->p.lwe_dim + 1;
+            FSC_CUDA_CHECK(cudaEventRecord(e->ev_fork, e->stream));          // staging buffers are free once earlier work is done
+            FSC_CUDA_CHECK(cudaStreamWaitEvent(e->copy_in, e->ev_fork, 0));
+            FSC_CUDA_CHECK(cudaStreamWaitEvent(e->copy_out, e->ev_fork, 0));
+            size_t k = 0;
+            for (size_t off = 0; off < count; off += chunk, ++k) {
+                const size_t c = std::min(chunk, count - off);
+                cudaEvent_t up = e->chunk_event(2 * k), done = e->chunk_event(2 * k + 1);
+                FSC_CUDA_CHECK(cudaMemcpyAsync(din + off * words, in_host + off * words, c * words * 8, cudaMemcpyHostToDevice, e->copy_in));
+                FSC_CUDA_CHECK(cudaEventRecord(up, e->copy_in));
+                FSC_CUDA_CHECK(cudaStreamWaitEvent(e->stream, up, 0));
+                e->keyswitch(din + off * words, e->scratch_small + off * nsmall, c);
+                e->pbs(e->scratch_small + off * nsmall, luts, di ? di + off : nullptr, dout + off * words, c);
+                FSC_CUDA_CHECK(cudaEventRecord(done, e->stream));
+                FSC_CUDA_CHECK(cudaStreamWaitEvent(e->copy_out, done, 0));
+                FSC_CUDA_CHECK(cudaMemcpyAsync(out_host + off * words, dout + off * words, c * words * 8, cudaMemcpyDeviceToHost, e->copy_out));
+            }
+            FSC_CUDA_CHECK(cudaEventRecord(e->ev_join, e->copy_out));
+            FSC_CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_join, 0));      // later work on the context's stream stays ordered
+        }
         FSC_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     }
     FSC_API_END(ctx)

@@ -145,7 +145,7 @@ def test_pbs_noise_matches_oracle_toy(gpu_ctx, oracle_keys, rng, acc_bits):
 def test_apply_lut_host_ragged_and_empty(gpu_ctx, oracle_keys, rng):
     K, ctx = oracle_keys("toy"), gpu_ctx("toy")
     luts = ctx.luts_from_tables(np.stack([np.arange(16), 15 - np.arange(16)]))
-    for count in (0, 1, 37):
+    for count in (0, 1, 37, 1500):      # 1500: more than one and a half kernel waves, so uploads / downloads run chunked on the copy streams
         m = rng.integers(0, 16, count).astype(np.uint64)
         idx = rng.integers(0, 2, count).astype(np.uint32)
         out = ctx.apply_lut_host(K.encrypt_msgs(m).reshape(count, 2049), luts, idx)
