@@ -57,6 +57,7 @@ Engine::Engine(const fsc_params& prm, int device, uintptr_t ext_stream) : p(prm)
     pbs_init_constants();
     const char* kv = getenv("FSC_KS_VARIANT");      // "simt" | "mma" (default)
     ks_variant = (kv && kv[0] == 's') ? 0 : (kv && kv[0] == 'm') ? 1 : 2;      // simt | mma | umma (default)
+    if (const char* ns = getenv("FSC_PBS_SPLIT")) use_split = atoi(ns) != 0;      // 0: narrow levels stay on the stream kernel
     if (const char* hw = getenv("FSC_HOST_CHUNK_WAVES")) host_chunk_waves = (size_t)atoi(hw);      // 0: one chunk, copies not overlapped
 }
 
@@ -122,7 +123,7 @@ void Engine::upload_keys(const uint64_t* bsk_std, size_t bsk_words, const uint64
     FSC_CUDA_CHECK(cudaMemcpyAsync(tmp, bsk_std, want_bsk * 8, cudaMemcpyHostToDevice, stream));
     FSC_CUDA_CHECK(cudaMemcpyAsync(ksk, ksk_h, want_ksk * 8, cudaMemcpyHostToDevice, stream));
     pbs_variant = pbs_variant_for((int)p.acc_bits);
-    if (pbs_variant == 2) launch_bsk_convert_stream(tmp, bsk_f, (int)n, stream);      // the stream kernel's key order
+    if (pbs_variant == 2 || pbs_variant == 4) launch_bsk_convert_stream(tmp, bsk_f, (int)n, stream);      // the stream kernel's key order
     else launch_bsk_convert(tmp, bsk_f, (int)n, stream);
     ++launches;
     if (pbs_variant == 3) {      // both kernels: second copy of the Fourier key in the stream kernel's order
@@ -217,7 +218,11 @@ void Engine::pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut
     if (!bsk_f) throw Error(FSC_ERR_NO_KEYS, "server keys not uploaded");
     // variant 3: narrow levels (at most two ciphertexts per SM: the latency-bound case) on the stream kernel, wide
     // batches on the ring kernel
-    if (pbs_variant == 3 && (int)count <= 2 * sm_count)
+    // variant 3: levels of at most one ciphertext per SM on the split kernel (four warps per ciphertext),
+    if (pbs_variant == 4 || (pbs_variant == 3 && use_split && (int)count <= sm_count))
+        launch_pbs_split((int)p.acc_bits, pbs_variant == 4 ? bsk_f : bsk_s, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d,
+                         lut_idx_dev, out_big, out_idx_dev, (int)count, stream);
+    else if (pbs_variant == 3 && (int)count <= 2 * sm_count)
         launch_pbs_stream((int)p.acc_bits, bsk_s, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, out_big,
                           out_idx_dev, (int)count, sm_count, stream);
     else if (pbs_variant == 2)
@@ -547,7 +552,7 @@ fsc_status fsc_launch_count(const fsc_ctx* ctx, uint64_t* out) {
 const char* fsc_pbs_kernel_name(const fsc_ctx* ctx) {
     if (!ctx) return "";
     const int v = ctx->eng->bsk_f ? ctx->eng->pbs_variant : fsc::pbs_variant_for((int)ctx->eng->p.acc_bits);
-    return v == 2 ? "pbs_stream_kernel" : v == 0 ? "pbs_pair_kernel" : "pbs_ring_kernel";
+    return v == 4 ? "pbs_split_kernel" : v == 2 ? "pbs_stream_kernel" : v == 0 ? "pbs_pair_kernel" : "pbs_ring_kernel";
 }
 
 fsc_status fsc_measure_fp64_peak(fsc_ctx* ctx, double* tflops) {

@@ -40,6 +40,9 @@ void launch_bsk_convert_stream(const uint64_t* bsk_std, void* bsk_fourier, int n
 void launch_pbs_stream(int acc_bits, const void* bsk_fourier, const uint64_t* in_small, int n, int base_log,
                        const uint64_t* luts, const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count,
                        int sm_count, cudaStream_t st);
+// pbs_split_kernel.cu (latency form for narrow levels: four warps per ciphertext; the stream kernel's key layout)
+void launch_pbs_split(int acc_bits, const void* bsk_fourier, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
+                      const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st);
 void launch_negacyclic_mul_stream(const uint64_t* a, const int64_t* b, uint64_t* c, int count, cudaStream_t st);
 // 0: pair, 1: ring, 2: stream, 3: ring (wide) + stream (narrow) (FSC_PBS_VARIANT, else by accumulator width);
 // fixed per context at key upload

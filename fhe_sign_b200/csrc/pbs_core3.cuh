@@ -1,0 +1,180 @@
+// pbs_core3.cuh — per-lane building blocks of the "split" blind rotation: the latency form for narrow PBS levels.
+//
+// A level of at most one ciphertext per SM is bound by the latency of one CMUX step, not by throughput: with two
+// warps per ciphertext (pbs_stream_kernel) each warp issues every instruction of a 1024-point transform alone and
+// half of the SM's sub-partitions idle.  Here FOUR warps share a ciphertext: warp (p, h) owns slots [16 h, 16 h + 16)
+// of polynomial p in every pass of the stream formulation (pbs_core2.cuh: same tables, same transposes, same key
+// order, same twist).  pass32's first butterfly level joins slot j with slot 16 + j — the only level that crosses the
+// two halves — and levels 2..5 stay inside a half, so a warp
+//   * reads all 32 inputs of its lane from shared memory (the partner warp's half was written there one block
+//     barrier earlier), forms its 16 level-1 outputs (lo + s hi for h = 0, lo - s hi for h = 1: 6 FP64 instructions
+//     per output instead of 8 per butterfly),
+//   * runs levels 2..5 on its 16 slots (the node constants of half h: entry 2^(L-2) + h 2^(L-3) + ...),
+//   * writes its 16 outputs to the buffer the next pass reads.
+// The Fourier-domain product feeds level 1 of inverse pass A directly: input slot s of that pass is
+// X_p[brev5 s] G[p][p] + X_{1-p}[brev5 s] G[1-p][p] (both spectra from shared memory), computed by both warps of a
+// polynomial — 256 redundant FP64 instructions that save one exchange and one barrier.
+// FP64 instructions per warp and CMUX step: 4 x (96 + 192) passes + 256 product + 64 twist + 128 rounding = 1 600
+// against 2 688, and a fourth of the shared-memory wavefronts of the other kernels matter here (one ciphertext per SM).
+//
+// h is a run-time value (one code path for the four warps, the loop body must not double): it enters through
+// addresses, the sign of level 1 and a warp-uniform branch around the single node of level 2.
+// Everything is __host__ __device__ with `lane` as an argument: tests/emu/pbs_emu3.cpp runs the same code on the CPU.
+#pragma once
+#include "pbs_core2.cuh"
+
+namespace fsc {
+
+constexpr int kSplitECplx = 32 * 32;             // exchange buffer of one polynomial: [slot][lane] complex, 16 KiB
+constexpr int kSplitTRow = 33;                   // transpose buffer row (complex), padded: conflict-free both ways
+constexpr int kSplitTCplx = 32 * kSplitTRow;     // [row][33] complex, 16.5 KiB
+
+// ---- the pass on one half ------------------------------------------------------------------------
+// ld(s): input slot s of the calling lane (s is a compile-time constant at every call site after unrolling)
+template <class LD, class SP>
+FSC_HD void split_pass(int h, const LD& ld, const SP& sp, cplx (&w)[16]) {
+    {   // level 1, (re, im) constant: the outputs of half h only
+        const double sg = h ? -1.0 : 1.0;
+        const cplx s = sp.get(0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const cplx lo = ld(j), hi = ld(16 + j);
+            const double tx = fma(-s.y, hi.y, s.x * hi.x);
+            const double ty = fma(s.y, hi.x, s.x * hi.y);
+            w[j].x = fma(sg, tx, lo.x);
+            w[j].y = fma(sg, ty, lo.y);
+        }
+    }
+    {   // level 2: node m = h, constant entry 1, the odd node (h = 1) multiplies by i s
+        const cplx s = sp.get(1);
+        if (!h) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const cplx lo = w[j], hi = w[8 + j];
+                const double qx = fma(-s.y, hi.y, hi.x);
+                const double qy = fma(s.y, hi.x, hi.y);
+                w[j].x = fma(s.x, qx, lo.x);      w[j].y = fma(s.x, qy, lo.y);
+                w[8 + j].x = fma(-s.x, qx, lo.x); w[8 + j].y = fma(-s.x, qy, lo.y);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const cplx lo = w[j], hi = w[8 + j];
+                const double qx = fma(-s.y, hi.y, hi.x);
+                const double qy = fma(s.y, hi.x, hi.y);
+                w[j].x = fma(-s.x, qy, lo.x);     w[j].y = fma(s.x, qx, lo.y);
+                w[8 + j].x = fma(s.x, qy, lo.x);  w[8 + j].y = fma(-s.x, qx, lo.y);
+            }
+        }
+    }
+#pragma unroll
+    for (int L = 3; L <= 5; ++L) {
+        const int half = 16 >> (L - 1);
+        const int ci0 = (1 << (L - 2)) + (h << (L - 3));      // pass32: entry 2^(L-2) + (m >> 1), m = h 2^(L-2) + mm
+#pragma unroll
+        for (int mm = 0; mm < (1 << (L - 2)); ++mm) {
+            const int base = mm * 2 * half;
+            const bool odd = mm & 1;
+            const cplx s = sp.get(ci0 + (mm >> 1));
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+                const cplx lo = w[base + j], hi = w[base + half + j];
+                const double qx = fma(-s.y, hi.y, hi.x);
+                const double qy = fma(s.y, hi.x, hi.y);
+                if (!odd) {
+                    w[base + j].x = fma(s.x, qx, lo.x);         w[base + j].y = fma(s.x, qy, lo.y);
+                    w[base + half + j].x = fma(-s.x, qx, lo.x); w[base + half + j].y = fma(-s.x, qy, lo.y);
+                } else {
+                    w[base + j].x = fma(-s.x, qy, lo.x);        w[base + j].y = fma(s.x, qx, lo.y);
+                    w[base + half + j].x = fma(s.x, qy, lo.x);  w[base + half + j].y = fma(-s.x, qx, lo.y);
+                }
+            }
+        }
+    }
+}
+
+// ---- stages around the passes (warp (p, h), lane) ---------------------------------------------------
+// head: digits of X^a acc - acc at folded indices lane + 32 j2, j2 in [16 h, 16 h + 16)  ->  E[j2][lane]
+template <typename AccT>
+FSC_HD void split_head(int lane, int h, const pair_t<AccT>* poly, int a, int base_log, cplx* E) {
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+        const int j2 = 16 * h + jj;
+        const int idx = lane + 32 * j2;
+        const pair_t<AccT> R = rotated_pair<AccT>(poly, idx, a);
+        const pair_t<AccT> O = poly[idx];
+        cplx z;
+        z.x = decomp_digit<AccT>((AccT)(R.x - O.x), base_log);
+        z.y = decomp_digit<AccT>((AccT)(R.y - O.y), base_log);
+        E[j2 * 32 + lane] = z;
+    }
+}
+struct SplitLoadE {          // input slot s of a pass fed by an exchange buffer
+    const cplx* e;           // E + lane
+    FSC_HD cplx operator()(int s) const { return e[s * 32]; }
+};
+struct SplitLoadT {          // input slot s of a pass fed by the transpose buffer: row `row`, column s
+    const cplx* t;           // T + row * kSplitTRow
+    FSC_HD cplx operator()(int s) const { return t[s]; }
+};
+// outputs of forward pass 1 / inverse pass A: slot pos = 16 h + jj goes to row brev5(pos), column lane
+FSC_HD void split_xp_store(int lane, int h, cplx* T, const cplx (&w)[16]) {
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) T[(brev5(jj) + h) * kSplitTRow + lane] = w[jj];      // brev5(16 h + jj) = brev5(jj) + h
+}
+// outputs of forward pass 2 (the spectrum, slot pos holds frequency brev5(pos)) -> E[pos][lane]
+FSC_HD void split_spec_store(int lane, int h, cplx* E, const cplx (&w)[16]) {
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) E[(16 * h + jj) * 32 + lane] = w[jj];
+}
+// input slot s (frequency k1 = s) of inverse pass A: both spectra times the GGSW column of polynomial p
+struct SplitLoadProduct {
+    const cplx* own;         // E_p + lane
+    const cplx* oth;         // E_{1-p} + lane
+    const cplx* g0;          // key half 0 (+ lane): [16 positions][4 g][32 lanes]
+    const cplx* g1;          // key half 1 (+ lane)
+    int g_own, g_oth;
+    FSC_HD cplx operator()(int s) const {
+        const int r = freq_pos(s);
+        const cplx* g = ((r >> 4) ? g1 : g0) + (r & 15) * 128;
+        const cplx x = own[brev5(s) * 32], o = oth[brev5(s) * 32];
+        const cplx gw = g[g_own * 32], go = g[g_oth * 32];
+        cplx y;
+        y.x = fma(-o.y, go.y, fma(o.x, go.x, fma(-x.y, gw.y, x.x * gw.x)));
+        y.y = fma(o.y, go.x, fma(o.x, go.y, fma(x.y, gw.x, x.x * gw.y)));
+        return y;
+    }
+};
+// tail: twist, rounding, accumulation of the 16 outputs of inverse pass B (slot pos <-> j2 = -brev5(pos) mod 32)
+template <typename AccT>
+FSC_HD void split_tail(int lane, int h, pair_t<AccT>* poly, const cplx* tw, const cplx (&y)[16]) {
+#pragma unroll
+    for (int b0 = 0; b0 < 16; b0 += 8) {
+        cplx t[8];
+        pair_t<AccT> O[8];
+        double re[8], im[8];
+        int idx[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int pos = 16 * h + b0 + u;
+            idx[u] = lane + 32 * ((32 - brev5(b0 + u) - h) & 31);      // tail_j2(16 h + jj)
+            t[u] = tw[pos * 32 + lane];
+            O[u] = poly[idx[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const cplx x = y[b0 + u];
+            re[u] = fma(-x.y, t[u].y, x.x * t[u].x);
+            im[u] = fma(x.y, t[u].x, x.x * t[u].y);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            O[u].x = (AccT)(O[u].x + to_acc_scaled<AccT>(re[u]));
+            O[u].y = (AccT)(O[u].y + to_acc_scaled<AccT>(im[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) poly[idx[u]] = O[u];
+    }
+}
+
+}  // namespace fsc

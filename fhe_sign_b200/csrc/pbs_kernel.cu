@@ -680,6 +680,7 @@ int pbs_variant_for(int acc_bits) {
     const char* e = getenv("FSC_PBS_VARIANT");
     if (e && e[0] == 'p') return 0;
     if (e && e[0] == 'r') return 1;
+    if (e && e[0] == 's' && e[1] == 'p') return 4;      // "split": the latency kernel at every width (tests)
     if (e && e[0] == 's') return 2;
     if (e && e[0] == 'a') return 3;
     return acc_bits == 32 ? 3 : 1;

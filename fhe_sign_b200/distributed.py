@@ -42,7 +42,7 @@ def make_all_gather(buffer_tensor, group=None, stream=None):
     return EXCHANGE_FN(_cb)
 
 
-def enable_level_sharding(ctx, stream, min_width=1184, capacity_blocks=1 << 16, group=None):
+def enable_level_sharding(ctx, stream, min_width=149, capacity_blocks=1 << 16, group=None):
     """Shard every PBS level of >= min_width requests across the ranks of the default process group.
 
     `stream` is the torch.cuda.Stream the context was created on (Context(..., stream=stream.cuda_stream)); it must

@@ -1,3 +1,5 @@
+#include <stdio.h>
+#include <stdlib.h>
 // mock_backend.cpp — TEST INFRASTRUCTURE.  A plaintext stand-in for the device side of the radix
 // layer (fsc::RadixBackend): every "ciphertext" is the integer it would decrypt to, modulo 32 (4
 // plaintext bits + the padding bit), and a bootstrap is the negacyclic table lookup a real PBS
@@ -60,6 +62,7 @@ public:
         ++sharded_levels;
     }
     void run_level(const std::vector<fsc::LevelReq>& reqs) override {
+        if (getenv("FSC_MOCK_TRACE")) fprintf(stderr, "level %zu\n", reqs.size());      // level widths, for schedule studies
         if (exchange.active(reqs.size())) { run_level_sharded(reqs); return; }
         std::vector<int> out(reqs.size());
         for (size_t i = 0; i < reqs.size(); ++i) {

@@ -122,3 +122,38 @@ def test_stream_blind_rotation_decrypts_like_oracle(emu2, orc, oracle_keys, rng,
     e_emu = (K.phase_big(out) - K.encode(table[m])).astype(np.int64).astype(np.float64)
     e_ref = (K.phase_big(ref) - K.encode(table[m])).astype(np.int64).astype(np.float64)
     assert e_emu.std() < 1.5 * e_ref.std()
+
+
+# ---- split formulation: four warps per ciphertext (pbs_core3.cuh, tests/emu/pbs_emu3.cpp) -----------------------
+@pytest.fixture(scope="module")
+def emu3():
+    so = os.path.join(HERE, "emu", "libpbs_emu3.so")
+    src = os.path.join(HERE, "emu", "pbs_emu3.cpp")
+    cores = [os.path.join(HERE, "..", "fhe_sign_b200", "csrc", f) for f in ("pbs_core.cuh", "pbs_core2.cuh", "pbs_core3.cuh")]
+    if not os.path.exists(so) or max(os.path.getmtime(f) for f in [src] + cores) > os.path.getmtime(so):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-march=x86-64-v3", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
+    E = C.CDLL(so)
+    vp = C.c_void_p
+    E.emu3_blind_rotate.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
+    return E
+
+
+@pytest.mark.parametrize("acc_bits", [64, 32])
+def test_split_blind_rotation_matches_stream_formulation(emu2, emu3, orc, oracle_keys, rng, acc_bits):
+    """The half-pass decomposition is the same arithmetic as pass32 on 32 slots up to the order of the product's
+    additions: outputs agree with the stream emulator to rounding noise and decrypt like the oracle."""
+    K = oracle_keys("toy")
+    n = K.params.lwe_dim
+    bf = np.empty(n * 32 * 4 * 32 * 2, dtype=np.float64)
+    emu2.emu2_convert_bsk(n, P(K.bsk), P(bf))
+    table = rng.integers(0, 16, 16).astype(np.uint64)
+    lut = K.make_lut(table)
+    m = rng.integers(0, 16, 32).astype(np.uint64)
+    small = K.keyswitch(K.encrypt_msgs(m))
+    out, out2 = np.empty((m.size, 2049), dtype=np.uint64), np.empty((m.size, 2049), dtype=np.uint64)
+    emu3.emu3_blind_rotate(acc_bits, n, K.params.pbs_base_log, P(bf), P(small), m.size, P(lut), P(out))
+    emu2.emu2_blind_rotate(acc_bits, n, K.params.pbs_base_log, P(bf), P(small), m.size, P(lut), P(out2))
+    assert (K.decrypt_msgs(out) == table[m]).all()
+    e3 = (K.phase_big(out) - K.encode(table[m])).astype(np.int64).astype(np.float64)
+    e2 = (K.phase_big(out2) - K.encode(table[m])).astype(np.int64).astype(np.float64)
+    assert e3.std() < 1.5 * e2.std()

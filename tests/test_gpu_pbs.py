@@ -78,7 +78,7 @@ def test_pbs_all_messages_all_luts(gpu_ctx, oracle_keys, rng, preset, acc_bits):
 
 
 @pytest.mark.parametrize("acc_bits", [32, 64])
-@pytest.mark.parametrize("variant", ["auto", "stream", "ring", "pair"])
+@pytest.mark.parametrize("variant", ["auto", "stream", "ring", "pair", "split"])
 def test_pbs_kernel_variants_all_widths(oracle_keys, orc, rng, variant, acc_bits, monkeypatch):
     """Every blind-rotation kernel (FSC_PBS_VARIANT) at batch widths that select each of its configurations
     (1, 2 and 3-4 ciphertexts per CTA, ragged last CTA): decrypted values equal the table, noise inside the budget.

@@ -33,7 +33,7 @@ def main():
     ctx = fsb.Context(fsb.Params.preset("2_2_gaussian", acc_bits=32), device=local, stream=stream.cuda_stream)
     ctx.upload_keys(K.bsk, K.ksk)
     if world > 1:
-        enable_level_sharding(ctx, stream, min_width=int(os.environ.get("FSC_SHARD_MIN", "1184")), capacity_blocks=1 << 16)
+        enable_level_sharding(ctx, stream, min_width=int(os.environ.get("FSC_SHARD_MIN", "149")), capacity_blocks=1 << 16)
     R = ctx.radix
     ck = OracleClientKey(K, seed=77)          # same seed on every rank: identical ciphertexts everywhere
     rnd = np.random.default_rng(5)
