@@ -32,19 +32,22 @@ constexpr int kSplitTCplx = 32 * kSplitTRow;     // [row][33] complex, 16.5 KiB
 // ---- the pass on one half ------------------------------------------------------------------------
 // ld(s): input slot s of the calling lane (s is a compile-time constant at every call site after unrolling)
 template <class LD, class SP>
-FSC_HD void split_pass(int h, const LD& ld, const SP& sp, cplx (&w)[16]) {
-    {   // level 1, (re, im) constant: the outputs of half h only
-        const double sg = h ? -1.0 : 1.0;
-        const cplx s = sp.get(0);
+FSC_HD void split_level1(int h, const LD& ld, const SP& sp, cplx (&w)[16]) {
+    // level 1, (re, im) constant: the outputs of half h only
+    const double sg = h ? -1.0 : 1.0;
+    const cplx s = sp.get(0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const cplx lo = ld(j), hi = ld(16 + j);
-            const double tx = fma(-s.y, hi.y, s.x * hi.x);
-            const double ty = fma(s.y, hi.x, s.x * hi.y);
-            w[j].x = fma(sg, tx, lo.x);
-            w[j].y = fma(sg, ty, lo.y);
-        }
+    for (int j = 0; j < 16; ++j) {
+        const cplx lo = ld(j), hi = ld(16 + j);
+        const double tx = fma(-s.y, hi.y, s.x * hi.x);
+        const double ty = fma(s.y, hi.x, s.x * hi.y);
+        w[j].x = fma(sg, tx, lo.x);
+        w[j].y = fma(sg, ty, lo.y);
     }
+}
+// levels 2..5 on the 16 slots of half h
+template <class SP>
+FSC_HD void split_levels25(int h, const SP& sp, cplx (&w)[16]) {
     {   // level 2: node m = h, constant entry 1, the odd node (h = 1) multiplies by i s
         const cplx s = sp.get(1);
         if (!h) {
@@ -91,6 +94,12 @@ FSC_HD void split_pass(int h, const LD& ld, const SP& sp, cplx (&w)[16]) {
             }
         }
     }
+}
+
+template <class LD, class SP>
+FSC_HD void split_pass(int h, const LD& ld, const SP& sp, cplx (&w)[16]) {
+    split_level1(h, ld, sp, w);
+    split_levels25(h, sp, w);
 }
 
 // ---- stages around the passes (warp (p, h), lane) ---------------------------------------------------
@@ -145,6 +154,45 @@ struct SplitLoadProduct {
         return y;
     }
 };
+// Product without the redundancy: warp h forms the products of input slots j and 16 + j for j in [8 h, 8 h + 8) only,
+// runs their eight level-1 butterflies of inverse pass A whole, keeps the output of its own half (local index j) and
+// hands the other one (same local index, other half) to its partner through X[h][j - 8 h][lane]; after a barrier
+// of the polynomial's two warps split_product_recv completes w with the partner's eight outputs.
+constexpr int kSplitXCplx = 2 * 8 * 32;          // exchange area of one polynomial, 8 KiB
+template <class SP>
+FSC_HD void split_product_send(int lane, int h, const SplitLoadProduct& ld, const SP& sp, cplx* X, cplx (&w)[16]) {
+    const cplx s = sp.get(0);
+    if (!h) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const cplx lo = ld(jj), hi = ld(16 + jj);
+            const double tx = fma(-s.y, hi.y, s.x * hi.x);
+            const double ty = fma(s.y, hi.x, s.x * hi.y);
+            w[jj].x = lo.x + tx; w[jj].y = lo.y + ty;
+            cplx o; o.x = lo.x - tx; o.y = lo.y - ty;
+            X[jj * 32 + lane] = o;
+        }
+    } else {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const cplx lo = ld(8 + jj), hi = ld(24 + jj);
+            const double tx = fma(-s.y, hi.y, s.x * hi.x);
+            const double ty = fma(s.y, hi.x, s.x * hi.y);
+            w[8 + jj].x = lo.x - tx; w[8 + jj].y = lo.y - ty;
+            cplx o; o.x = lo.x + tx; o.y = lo.y + ty;
+            X[(8 + jj) * 32 + lane] = o;
+        }
+    }
+}
+FSC_HD void split_product_recv(int lane, int h, const cplx* X, cplx (&w)[16]) {
+    if (!h) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) w[8 + jj] = X[(8 + jj) * 32 + lane];
+    } else {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) w[jj] = X[jj * 32 + lane];
+    }
+}
 // tail: twist, rounding, accumulation of the 16 outputs of inverse pass B (slot pos <-> j2 = -brev5(pos) mod 32)
 template <typename AccT>
 FSC_HD void split_tail(int lane, int h, pair_t<AccT>* poly, const cplx* tw, const cplx (&y)[16]) {

@@ -5,7 +5,7 @@
 // sub-partition, and half of the SM's FP64 pipes idle; this kernel gives it four — warp (p, h) owns slots
 // [16 h, 16 h + 16) of GLWE polynomial p in every pass (pbs_core3.cuh) — so every sub-partition issues half of the
 // instructions per step.  Same tables, same Fourier key layout and ring as the stream kernel; everything that crosses
-// warps goes through shared memory and five block barriers per step:
+// warps goes through shared memory and five barriers per step (two of the block, three of a polynomial's two warps):
 //
 //      head (16 slots)                       -> E_p [slot][lane]          | barrier
 //      pass 0 on half h                      -> T_p (transpose buffer)    | barrier
@@ -25,10 +25,55 @@
 #include "fsc_internal.h"
 #include "tma_ring.cuh"
 #include "pbs_stream_tables.cuh"
+#include "pbs_head.cuh"
 
 namespace fsc {
 
-template <typename AccT, int NH>
+// head of half h for the 32-bit accumulator in the ALU / FMA-pipe form of stream_head_u32 (pbs_head.cuh): same result
+// as split_head<uint32_t>, no predicates, no conversion unit
+__device__ __forceinline__ void split_head_u32(int lane, int h, const pair_t<uint32_t>* poly, int a, int base_log, cplx* E) {
+    const int sh = 32 - base_log;
+    const int half = 1 << (sh - 1);
+    const int base = (lane - a) & 4095;
+    const int q0 = base >> 10, q1 = (q0 + 1) & 3;
+    const int swA = q0 & 1;
+    const int sxA = 1 - (q0 & 2), syA = 1 - ((q0 ^ (q0 << 1)) & 2);
+    const int sxB = 1 - (q1 & 2), syB = 1 - ((q1 ^ (q1 << 1)) & 2);
+    const int dsx = sxB - sxA, dsy = syB - syA;
+    const unsigned b8 = ((unsigned)(base & 1023) << 3) + 4096u * h;
+    const char* pb = reinterpret_cast<const char*>(poly);
+    const char* po = pb + lane * 8 + 4096 * h;
+    cplx* e = E + (16 * h) * 32 + lane;
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+        const unsigned u = b8 + 256u * jj;                       // byte offset of the rotated pair, bit 13 = crossed
+        const int c = (int)(u >> 13);
+        const uint2 P = *reinterpret_cast<const uint2*>(pb + (u & 8191u));
+        const uint2 O = *reinterpret_cast<const uint2*>(po + 256 * jj);
+        const int sw = swA ^ c;
+        const int sx = imad(c, dsx, sxA), sy = imad(c, dsy, syA);
+        const int d = (int)(P.y - P.x);
+        const int px = imad(sw, d, (int)P.x);
+        const int py = (int)(P.x + P.y) - px;
+        const int dx = imad(px, sx, half - (int)O.x);
+        const int dy = imad(py, sy, half - (int)O.y);
+        cplx z;
+        z.x = __hiloint2double(0x43300000, (dx >> sh) ^ (int)0x80000000) - 4503601774854144.0;
+        z.y = __hiloint2double(0x43300000, (dy >> sh) ^ (int)0x80000000) - 4503601774854144.0;
+        e[jj * 32] = z;
+    }
+}
+template <typename AccT>
+__device__ __forceinline__ void split_head_dev(int lane, int h, const pair_t<AccT>* poly, int a, int base_log, cplx* E) {
+    if constexpr (sizeof(AccT) == 4) split_head_u32(lane, h, poly, a, base_log, E);
+    else split_head<AccT>(lane, h, poly, a, base_log, E);
+}
+__device__ __forceinline__ void poly_barrier(int p) {      // the two warps of one polynomial
+    if (p) asm volatile("bar.sync 2, 64;" ::: "memory");
+    else asm volatile("bar.sync 1, 64;" ::: "memory");
+}
+
+template <typename AccT, int NH, bool PX>
 __global__ void __launch_bounds__(128, 1) pbs_split_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                             int n, int base_log, const uint64_t* __restrict__ luts,
                                                             const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
@@ -40,7 +85,8 @@ __global__ void __launch_bounds__(128, 1) pbs_split_kernel(const cplx* __restric
     cplx* T_all = E_all + 2 * kSplitECplx;
     cplx* ring = T_all + 2 * kSplitTCplx;
     cplx* tabs = ring + (size_t)NH * kHalfCplx;
-    uint64_t* full = reinterpret_cast<uint64_t*>(tabs + kTabCplx);
+    cplx* X_all = tabs + kTabCplx;                     // PX: level-1 outputs handed to the partner warp after the product
+    uint64_t* full = reinterpret_cast<uint64_t*>(X_all + (PX ? 2 * kSplitXCplx : 0));
     uint64_t* empty = full + NH;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     static_assert(NH >= 2, "the ring must hold a whole step");
@@ -91,12 +137,14 @@ __global__ void __launch_bounds__(128, 1) pbs_split_kernel(const cplx* __restric
         if ((i & 31) == 0) a_chunk = (i + lane < n) ? modswitch(ct[i + lane]) : 0;
         const int a = __shfl_sync(0xffffffffu, a_chunk, i & 31);
 
-        split_head<AccT>(lane, h, acc, a, base_log, E);
-        __syncthreads();
+        // E_p and T_p are written and read by the two warps of polynomial p, except for the product, which reads both
+        // spectra: block barriers on either side of the product, polynomial barriers elsewhere
+        split_head_dev<AccT>(lane, h, acc, a, base_log, E);
+        poly_barrier(p);
         FSC_POLL();
         split_pass(h, SplitLoadE{E + lane}, c0, w);
         split_xp_store(lane, h, T, w);
-        __syncthreads();
+        poly_barrier(p);
         split_pass(h, SplitLoadT{T + lane * kSplitTRow}, c1, w);
         split_spec_store(lane, h, E, w);
         // both halves of this step must have been requested before any warp sleeps on them; the stages the producer
@@ -115,34 +163,46 @@ __global__ void __launch_bounds__(128, 1) pbs_split_kernel(const cplx* __restric
             if (++stage == NH) { stage = 0; phase ^= 1; }
             const SplitLoadProduct ld{E + lane, E_oth + lane, ring + (size_t)st0 * kHalfCplx + lane,
                                       ring + (size_t)st1 * kHalfCplx + lane, 3 * p, 2 - p};
-            split_pass(h, ld, c2, w);
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(empty + st0); mbar_arrive(empty + st1); }
+            if constexpr (PX) {
+                cplx* X = X_all + (size_t)p * kSplitXCplx;
+                split_product_send(lane, h, ld, c2, X, w);
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(empty + st0); mbar_arrive(empty + st1); }
+                poly_barrier(p);
+                split_product_recv(lane, h, X, w);
+                split_levels25(h, c2, w);
+            } else {
+                split_pass(h, ld, c2, w);
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(empty + st0); mbar_arrive(empty + st1); }
+            }
         }
         split_xp_store(lane, h, T, w);
         __syncthreads();
         FSC_POLL();
         split_pass(h, SplitLoadT{T + row_inv * kSplitTRow}, c3, w);
         split_tail<AccT>(lane, h, acc, tabs + kTabTwist, w);
-        __syncthreads();
+        poly_barrier(p);
     }
 #undef FSC_POLL
+    __syncthreads();
 
     uint64_t* out = out_big + (size_t)(out_idx ? out_idx[c] : c) * (kN + 1);
     for (int j = threadIdx.x; j <= kN; j += 128) out[j] = extract_word<AccT>(acc_all, acc_all + 1024, j);
 }
 
-template <typename AccT, int NH>
+template <typename AccT, int NH, bool PX>
 static void launch_pbs_split_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
                                const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     const size_t smem = (size_t)2 * 1024 * sizeof(pair_t<AccT>) + (size_t)2 * (kSplitECplx + kSplitTCplx) * sizeof(cplx) +
-                        (size_t)NH * kHalfCplx * sizeof(cplx) + (size_t)kTabCplx * sizeof(cplx) + 2 * NH * sizeof(uint64_t);
+                        (size_t)NH * kHalfCplx * sizeof(cplx) + (size_t)kTabCplx * sizeof(cplx) + 2 * NH * sizeof(uint64_t) +
+                        (PX ? (size_t)2 * kSplitXCplx * sizeof(cplx) : 0);
     static bool configured = false;
     if (!configured) {
-        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_split_kernel<AccT, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_split_kernel<AccT, NH, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    pbs_split_kernel<AccT, NH><<<count, 128, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts, lut_idx,
+    pbs_split_kernel<AccT, NH, PX><<<count, 128, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts, lut_idx,
                                                          out_big, out_idx, count, stream_tables<AccT>());
 }
 
@@ -150,8 +210,17 @@ static void launch_pbs_split_t(const void* bsk_f, const uint64_t* in_small, int 
 void launch_pbs_split(int acc_bits, const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
                       const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     if (count <= 0) return;
-    if (acc_bits == 32) launch_pbs_split_t<uint32_t, 3>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
-    else launch_pbs_split_t<uint64_t, 2>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
+#define FSC_SPLIT(ACC, NH, PX) launch_pbs_split_t<ACC, NH, PX>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st)
+    const char* cfg = getenv("FSC_SPLIT_CFG");      // experiment switch: "3r" = three-stage ring + redundant product, "2r", "2x"
+    if (acc_bits == 32) {
+        if (cfg && cfg[0] == '3') FSC_SPLIT(uint32_t, 3, false);
+        else if (cfg && cfg[0] == '2' && cfg[1] == 'r') FSC_SPLIT(uint32_t, 2, false);
+        else FSC_SPLIT(uint32_t, 2, true);
+    } else {
+        if (cfg && cfg[1] == 'r') FSC_SPLIT(uint64_t, 2, false);
+        else FSC_SPLIT(uint64_t, 2, true);
+    }
+#undef FSC_SPLIT
 }
 
 }  // namespace fsc

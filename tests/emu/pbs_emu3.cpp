@@ -24,10 +24,10 @@ struct Tables {
 const Tables& tables() { static Tables T; return T; }
 
 template <typename AccT>
-void blind_rotate(int n, int base_log, const cplx* bsk_f, const uint64_t* ct, const uint64_t* lut, uint64_t* out) {
+void blind_rotate(bool px, int n, int base_log, const cplx* bsk_f, const uint64_t* ct, const uint64_t* lut, uint64_t* out) {
     const Tables& T = tables();
     std::vector<pair_t<AccT>> acc(2 * 1024);
-    std::vector<cplx> E(2 * kSplitECplx), Tb(2 * kSplitTCplx);
+    std::vector<cplx> E(2 * kSplitECplx), Tb(2 * kSplitTCplx), X(2 * kSplitXCplx);
     static cplx w[2][2][32][16];          // registers of warp (p, h), lane
     const int b = modswitch(ct[n]);
     for (int idx = 0; idx < 1024; ++idx) { acc[idx].x = 0; acc[idx].y = 0; acc[1024 + idx] = lut_pair<AccT>(lut, idx, b); }
@@ -44,9 +44,21 @@ void blind_rotate(int n, int base_log, const cplx* bsk_f, const uint64_t* ct, co
         ALL split_spec_store(l, h, E.data() + p * kSplitECplx, w[p][h][l]);
         // barrier
         const cplx* g = bsk_f + (size_t)i * 32 * 4 * 32;
-        ALL {
-            SplitLoadProduct ld{E.data() + p * kSplitECplx + l, E.data() + (1 - p) * kSplitECplx + l, g + l, g + 16 * 4 * 32 + l, 3 * p, 2 - p};
-            split_pass(h, ld, StridedConsts{&T.t[2][0][l], 32}, w[p][h][l]);
+        if (!px) {      // product by both warps of a polynomial, feeding level 1 directly
+            ALL {
+                SplitLoadProduct ld{E.data() + p * kSplitECplx + l, E.data() + (1 - p) * kSplitECplx + l, g + l, g + 16 * 4 * 32 + l, 3 * p, 2 - p};
+                split_pass(h, ld, StridedConsts{&T.t[2][0][l], 32}, w[p][h][l]);
+            }
+        } else {        // product split between the two warps, level-1 outputs of the other half exchanged
+            ALL {
+                SplitLoadProduct ld{E.data() + p * kSplitECplx + l, E.data() + (1 - p) * kSplitECplx + l, g + l, g + 16 * 4 * 32 + l, 3 * p, 2 - p};
+                split_product_send(l, h, ld, StridedConsts{&T.t[2][0][l], 32}, X.data() + p * kSplitXCplx, w[p][h][l]);
+            }
+            // barrier
+            ALL {
+                split_product_recv(l, h, X.data() + p * kSplitXCplx, w[p][h][l]);
+                split_levels25(h, StridedConsts{&T.t[2][0][l], 32}, w[p][h][l]);
+            }
         }
         ALL split_xp_store(l, h, Tb.data() + p * kSplitTCplx, w[p][h][l]);
         // barrier
@@ -60,12 +72,12 @@ void blind_rotate(int n, int base_log, const cplx* bsk_f, const uint64_t* ct, co
 }  // namespace
 
 extern "C" {
-void emu3_blind_rotate(int acc_bits, int n, int base_log, const double* bsk_f, const uint64_t* cts, int count,
+void emu3_blind_rotate(int acc_bits, int px, int n, int base_log, const double* bsk_f, const uint64_t* cts, int count,
                        const uint64_t* lut, uint64_t* out) {
     const cplx* f = reinterpret_cast<const cplx*>(bsk_f);
     for (int c = 0; c < count; ++c) {
-        if (acc_bits == 64) blind_rotate<uint64_t>(n, base_log, f, cts + (size_t)c * (n + 1), lut, out + (size_t)c * (kN + 1));
-        else blind_rotate<uint32_t>(n, base_log, f, cts + (size_t)c * (n + 1), lut, out + (size_t)c * (kN + 1));
+        if (acc_bits == 64) blind_rotate<uint64_t>(px != 0, n, base_log, f, cts + (size_t)c * (n + 1), lut, out + (size_t)c * (kN + 1));
+        else blind_rotate<uint32_t>(px != 0, n, base_log, f, cts + (size_t)c * (n + 1), lut, out + (size_t)c * (kN + 1));
     }
 }
 }

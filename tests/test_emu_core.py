@@ -134,14 +134,16 @@ def emu3():
         subprocess.check_call(["/usr/bin/g++", "-O2", "-march=x86-64-v3", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
     E = C.CDLL(so)
     vp = C.c_void_p
-    E.emu3_blind_rotate.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
+    E.emu3_blind_rotate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
     return E
 
 
+@pytest.mark.parametrize("px", [0, 1])
 @pytest.mark.parametrize("acc_bits", [64, 32])
-def test_split_blind_rotation_matches_stream_formulation(emu2, emu3, orc, oracle_keys, rng, acc_bits):
+def test_split_blind_rotation_matches_stream_formulation(emu2, emu3, orc, oracle_keys, rng, acc_bits, px):
     """The half-pass decomposition is the same arithmetic as pass32 on 32 slots up to the order of the product's
-    additions: outputs agree with the stream emulator to rounding noise and decrypt like the oracle."""
+    additions: outputs agree with the stream emulator to rounding noise and decrypt like the oracle.
+    px = 1: the Fourier-domain product split between the two warps of a polynomial (what the kernel runs)."""
     K = oracle_keys("toy")
     n = K.params.lwe_dim
     bf = np.empty(n * 32 * 4 * 32 * 2, dtype=np.float64)
@@ -151,7 +153,7 @@ def test_split_blind_rotation_matches_stream_formulation(emu2, emu3, orc, oracle
     m = rng.integers(0, 16, 32).astype(np.uint64)
     small = K.keyswitch(K.encrypt_msgs(m))
     out, out2 = np.empty((m.size, 2049), dtype=np.uint64), np.empty((m.size, 2049), dtype=np.uint64)
-    emu3.emu3_blind_rotate(acc_bits, n, K.params.pbs_base_log, P(bf), P(small), m.size, P(lut), P(out))
+    emu3.emu3_blind_rotate(acc_bits, px, n, K.params.pbs_base_log, P(bf), P(small), m.size, P(lut), P(out))
     emu2.emu2_blind_rotate(acc_bits, n, K.params.pbs_base_log, P(bf), P(small), m.size, P(lut), P(out2))
     assert (K.decrypt_msgs(out) == table[m]).all()
     e3 = (K.phase_big(out) - K.encode(table[m])).astype(np.int64).astype(np.float64)
