@@ -33,16 +33,22 @@ constexpr int kSplitTCplx = 32 * kSplitTRow;     // [row][33] complex, 16.5 KiB
 // ld(s): input slot s of the calling lane (s is a compile-time constant at every call site after unrolling)
 template <class LD, class SP>
 FSC_HD void split_level1(int h, const LD& ld, const SP& sp, cplx (&w)[16]) {
-    // level 1, (re, im) constant: the outputs of half h only
+    // level 1, (re, im) constant: the outputs of half h only.  Loads in batches of 16 ahead of their arithmetic: a warp
+    // is alone on its sub-partition here, nothing else hides the shared-memory latency
     const double sg = h ? -1.0 : 1.0;
     const cplx s = sp.get(0);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const cplx lo = ld(j), hi = ld(16 + j);
-        const double tx = fma(-s.y, hi.y, s.x * hi.x);
-        const double ty = fma(s.y, hi.x, s.x * hi.y);
-        w[j].x = fma(sg, tx, lo.x);
-        w[j].y = fma(sg, ty, lo.y);
+    for (int j0 = 0; j0 < 16; j0 += 8) {
+        cplx lo[8], hi[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { lo[u] = ld(j0 + u); hi[u] = ld(16 + j0 + u); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double tx = fma(-s.y, hi[u].y, s.x * hi[u].x);
+            const double ty = fma(s.y, hi[u].x, s.x * hi[u].y);
+            w[j0 + u].x = fma(sg, tx, lo[u].x);
+            w[j0 + u].y = fma(sg, ty, lo[u].y);
+        }
     }
 }
 // levels 2..5 on the 16 slots of half h
@@ -143,16 +149,22 @@ struct SplitLoadProduct {
     const cplx* g0;          // key half 0 (+ lane): [16 positions][4 g][32 lanes]
     const cplx* g1;          // key half 1 (+ lane)
     int g_own, g_oth;
-    FSC_HD cplx operator()(int s) const {
+    struct In { cplx x, o, gw, go; };
+    FSC_HD In load(int s) const {
         const int r = freq_pos(s);
         const cplx* g = ((r >> 4) ? g1 : g0) + (r & 15) * 128;
-        const cplx x = own[brev5(s) * 32], o = oth[brev5(s) * 32];
-        const cplx gw = g[g_own * 32], go = g[g_oth * 32];
+        In v;
+        v.x = own[brev5(s) * 32]; v.o = oth[brev5(s) * 32];
+        v.gw = g[g_own * 32]; v.go = g[g_oth * 32];
+        return v;
+    }
+    static FSC_HD cplx mul(const In& v) {
         cplx y;
-        y.x = fma(-o.y, go.y, fma(o.x, go.x, fma(-x.y, gw.y, x.x * gw.x)));
-        y.y = fma(o.y, go.x, fma(o.x, go.y, fma(x.y, gw.x, x.x * gw.y)));
+        y.x = fma(-v.o.y, v.go.y, fma(v.o.x, v.go.x, fma(-v.x.y, v.gw.y, v.x.x * v.gw.x)));
+        y.y = fma(v.o.y, v.go.x, fma(v.o.x, v.go.y, fma(v.x.y, v.gw.x, v.x.x * v.gw.y)));
         return y;
     }
+    FSC_HD cplx operator()(int s) const { return mul(load(s)); }
 };
 // Product without the redundancy: warp h forms the products of input slots j and 16 + j for j in [8 h, 8 h + 8) only,
 // runs their eight level-1 butterflies of inverse pass A whole, keeps the output of its own half (local index j) and
@@ -162,25 +174,38 @@ constexpr int kSplitXCplx = 2 * 8 * 32;          // exchange area of one polynom
 template <class SP>
 FSC_HD void split_product_send(int lane, int h, const SplitLoadProduct& ld, const SP& sp, cplx* X, cplx (&w)[16]) {
     const cplx s = sp.get(0);
+    constexpr int B = 4;                      // slot pairs per batch: 8 B loads in flight ahead of the arithmetic
     if (!h) {
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-            const cplx lo = ld(jj), hi = ld(16 + jj);
-            const double tx = fma(-s.y, hi.y, s.x * hi.x);
-            const double ty = fma(s.y, hi.x, s.x * hi.y);
-            w[jj].x = lo.x + tx; w[jj].y = lo.y + ty;
-            cplx o; o.x = lo.x - tx; o.y = lo.y - ty;
-            X[jj * 32 + lane] = o;
+        for (int j0 = 0; j0 < 8; j0 += B) {
+            SplitLoadProduct::In a[B], b[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) { a[u] = ld.load(j0 + u); b[u] = ld.load(16 + j0 + u); }
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                const cplx lo = SplitLoadProduct::mul(a[u]), hi = SplitLoadProduct::mul(b[u]);
+                const double tx = fma(-s.y, hi.y, s.x * hi.x);
+                const double ty = fma(s.y, hi.x, s.x * hi.y);
+                w[j0 + u].x = lo.x + tx; w[j0 + u].y = lo.y + ty;
+                cplx o; o.x = lo.x - tx; o.y = lo.y - ty;
+                X[(j0 + u) * 32 + lane] = o;
+            }
         }
     } else {
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-            const cplx lo = ld(8 + jj), hi = ld(24 + jj);
-            const double tx = fma(-s.y, hi.y, s.x * hi.x);
-            const double ty = fma(s.y, hi.x, s.x * hi.y);
-            w[8 + jj].x = lo.x - tx; w[8 + jj].y = lo.y - ty;
-            cplx o; o.x = lo.x + tx; o.y = lo.y + ty;
-            X[(8 + jj) * 32 + lane] = o;
+        for (int j0 = 0; j0 < 8; j0 += B) {
+            SplitLoadProduct::In a[B], b[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) { a[u] = ld.load(8 + j0 + u); b[u] = ld.load(24 + j0 + u); }
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                const cplx lo = SplitLoadProduct::mul(a[u]), hi = SplitLoadProduct::mul(b[u]);
+                const double tx = fma(-s.y, hi.y, s.x * hi.x);
+                const double ty = fma(s.y, hi.x, s.x * hi.y);
+                w[8 + j0 + u].x = lo.x - tx; w[8 + j0 + u].y = lo.y - ty;
+                cplx o; o.x = lo.x + tx; o.y = lo.y + ty;
+                X[(8 + j0 + u) * 32 + lane] = o;
+            }
         }
     }
 }

@@ -44,12 +44,19 @@ __device__ __forceinline__ void split_head_u32(int lane, int h, const pair_t<uin
     const char* pb = reinterpret_cast<const char*>(poly);
     const char* po = pb + lane * 8 + 4096 * h;
     cplx* e = E + (16 * h) * 32 + lane;
+    // all 32 loads first: the warp is alone on its sub-partition, nothing else would hide their latency
+    uint2 Pv[16], Ov[16];
 #pragma unroll
     for (int jj = 0; jj < 16; ++jj) {
         const unsigned u = b8 + 256u * jj;                       // byte offset of the rotated pair, bit 13 = crossed
+        Pv[jj] = *reinterpret_cast<const uint2*>(pb + (u & 8191u));
+        Ov[jj] = *reinterpret_cast<const uint2*>(po + 256 * jj);
+    }
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+        const unsigned u = b8 + 256u * jj;
         const int c = (int)(u >> 13);
-        const uint2 P = *reinterpret_cast<const uint2*>(pb + (u & 8191u));
-        const uint2 O = *reinterpret_cast<const uint2*>(po + 256 * jj);
+        const uint2 P = Pv[jj], O = Ov[jj];
         const int sw = swA ^ c;
         const int sx = imad(c, dsx, sxA), sy = imad(c, dsy, syA);
         const int d = (int)(P.y - P.x);
