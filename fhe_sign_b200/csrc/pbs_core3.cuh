@@ -124,6 +124,11 @@ FSC_HD void split_head(int lane, int h, const pair_t<AccT>* poly, int a, int bas
         E[j2 * 32 + lane] = z;
     }
 }
+struct SplitLoadS {          // input slot s at base[s * stride]: run-time stride, one code path for E- and T-fed passes
+    const cplx* base;
+    int stride;
+    FSC_HD cplx operator()(int s) const { return base[s * stride]; }
+};
 struct SplitLoadE {          // input slot s of a pass fed by an exchange buffer
     const cplx* e;           // E + lane
     FSC_HD cplx operator()(int s) const { return e[s * 32]; }
@@ -155,6 +160,20 @@ struct SplitLoadProduct {
         const cplx* g = ((r >> 4) ? g1 : g0) + (r & 15) * 128;
         In v;
         v.x = own[brev5(s) * 32]; v.o = oth[brev5(s) * 32];
+        v.gw = g[g_own * 32]; v.go = g[g_oth * 32];
+        return v;
+    }
+    // the same for slot jj + 8 h + 16 b with h at run time (jj < 8 and b compile-time constants): the spectrum index is
+    // affine in h (brev5(s + 8) = brev5(s) + 2), the key address is one of two compile-time offsets
+    FSC_HD In load_rt(int jj, int b, int h) const {
+        const int sA = jj + 16 * b, sB = sA + 8;
+        const int rA = freq_pos(sA), rB = freq_pos(sB);
+        const cplx* gA = ((rA >> 4) ? g1 : g0) + (rA & 15) * 128;
+        const cplx* gB = ((rB >> 4) ? g1 : g0) + (rB & 15) * 128;
+        const cplx* g = h ? gB : gA;
+        const int si = (brev5(sA) + 2 * h) * 32;
+        In v;
+        v.x = own[si]; v.o = oth[si];
         v.gw = g[g_own * 32]; v.go = g[g_oth * 32];
         return v;
     }
@@ -217,6 +236,36 @@ FSC_HD void split_product_recv(int lane, int h, const cplx* X, cplx (&w)[16]) {
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) w[jj] = X[jj * 32 + lane];
     }
+}
+// The same with h at run time (one code path for both warps, the loop body must stay inside the instruction cache):
+// every level-1 output goes through X2[half][local index][lane], the warp of half h reads its 16 back after the barrier.
+constexpr int kSplitX2Cplx = 2 * 16 * 32;        // 16 KiB per polynomial
+template <class SP>
+FSC_HD void split_product_send2(int lane, int h, const SplitLoadProduct& ld, const SP& sp, cplx* X2) {
+    const cplx s = sp.get(0);
+    cplx* x = X2 + (8 * h) * 32 + lane;
+#pragma unroll
+    for (int j0 = 0; j0 < 8; j0 += 4) {
+        SplitLoadProduct::In a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { a[u] = ld.load_rt(j0 + u, 0, h); b[u] = ld.load_rt(j0 + u, 1, h); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const cplx lo = SplitLoadProduct::mul(a[u]), hi = SplitLoadProduct::mul(b[u]);
+            const double tx = fma(-s.y, hi.y, s.x * hi.x);
+            const double ty = fma(s.y, hi.x, s.x * hi.y);
+            cplx o0, o1;
+            o0.x = lo.x + tx; o0.y = lo.y + ty;
+            o1.x = lo.x - tx; o1.y = lo.y - ty;
+            x[(j0 + u) * 32] = o0;                 // slot 8 h + j: half 0, local index 8 h + j
+            x[512 + (j0 + u) * 32] = o1;           // slot 16 + 8 h + j: half 1, same local index
+        }
+    }
+}
+FSC_HD void split_product_recv2(int lane, int h, const cplx* X2, cplx (&w)[16]) {
+    const cplx* x = X2 + h * 512 + lane;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w[j] = x[j * 32];
 }
 // tail: twist, rounding, accumulation of the 16 outputs of inverse pass B (slot pos <-> j2 = -brev5(pos) mod 32)
 template <typename AccT>

@@ -80,7 +80,7 @@ __device__ __forceinline__ void poly_barrier(int p) {      // the two warps of o
     else asm volatile("bar.sync 1, 64;" ::: "memory");
 }
 
-template <typename AccT, int NH, bool PX>
+template <typename AccT, int NH, int PX>
 __global__ void __launch_bounds__(128, 1) pbs_split_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                             int n, int base_log, const uint64_t* __restrict__ luts,
                                                             const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(128, 1) pbs_split_kernel(const cplx* __restric
     cplx* ring = T_all + 2 * kSplitTCplx;
     cplx* tabs = ring + (size_t)NH * kHalfCplx;
     cplx* X_all = tabs + kTabCplx;                     // PX: level-1 outputs handed to the partner warp after the product
-    uint64_t* full = reinterpret_cast<uint64_t*>(X_all + (PX ? 2 * kSplitXCplx : 0));
+    uint64_t* full = reinterpret_cast<uint64_t*>(X_all + (PX == 2 ? 2 * kSplitX2Cplx : PX == 1 ? 2 * kSplitXCplx : 0));
     uint64_t* empty = full + NH;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     static_assert(NH >= 2, "the ring must hold a whole step");
@@ -144,6 +144,57 @@ __global__ void __launch_bounds__(128, 1) pbs_split_kernel(const cplx* __restric
         if ((i & 31) == 0) a_chunk = (i + lane < n) ? modswitch(ct[i + lane]) : 0;
         const int a = __shfl_sync(0xffffffffu, a_chunk, i & 31);
 
+        if constexpr (PX == 2) {
+            // Rolled form (FSC_SPLIT_CFG=22, comparison): ONE copy of level 1 (strided loads), of levels 2..5 and of the
+            // transpose store serves the four passes, the product runs with the half index at run time: 2 300 instructions
+            // in the kernel instead of 3 350.  Measured 1-3 % slower than the unrolled form (3.88 against 3.86 ms at 148
+            // blocks): the instruction cache is not what bounds four warps per SM.
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                const StridedConsts sp{tabs + (q == 0 ? kTabU0 : q == 1 ? kTabL1 + lane : q == 2 ? kTabU2 : kTabL3 + lane), (q & 1) ? 32 : 1};
+                if (q == 0) {
+                    split_head_dev<AccT>(lane, h, acc, a, base_log, E);
+                    poly_barrier(p);
+                    FSC_POLL();
+                }
+                if (q != 2) {
+                    const SplitLoadS ld{q == 0 ? E + lane : T + (q == 1 ? lane : row_inv) * kSplitTRow, q == 0 ? 32 : 1};
+                    split_level1(h, ld, sp, w);
+                } else {
+                    const int st0 = stage;
+                    mbar_wait(full + stage, phase);
+                    if (++stage == NH) { stage = 0; phase ^= 1; }
+                    const int st1 = stage;
+                    mbar_wait(full + stage, phase);
+                    if (++stage == NH) { stage = 0; phase ^= 1; }
+                    const SplitLoadProduct ld{E + lane, E_oth + lane, ring + (size_t)st0 * kHalfCplx + lane,
+                                              ring + (size_t)st1 * kHalfCplx + lane, 3 * p, 2 - p};
+                    cplx* X2 = X_all + (size_t)p * kSplitX2Cplx;
+                    split_product_send2(lane, h, ld, sp, X2);
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(empty + st0); mbar_arrive(empty + st1); }
+                    poly_barrier(p);
+                    split_product_recv2(lane, h, X2, w);
+                }
+                split_levels25(h, sp, w);
+                if (!(q & 1)) {
+                    split_xp_store(lane, h, T, w);
+                    if (q == 0) poly_barrier(p);
+                    else { __syncthreads(); FSC_POLL(); }
+                } else if (q == 1) {
+                    split_spec_store(lane, h, E, w);
+                    if (producer) {      // both halves of this step requested before any warp sleeps on them (see below)
+                        while (prod.next_h < 2 * (i + 1) && prod.next_h < total_halves)
+                            prod.poll(lane, bsk_f, ring, full, empty, total_halves);
+                    }
+                    __syncthreads();
+                } else {
+                    split_tail<AccT>(lane, h, acc, tabs + kTabTwist, w);
+                    poly_barrier(p);
+                }
+            }
+            continue;
+        }
         // E_p and T_p are written and read by the two warps of polynomial p, except for the product, which reads both
         // spectra: block barriers on either side of the product, polynomial barriers elsewhere
         split_head_dev<AccT>(lane, h, acc, a, base_log, E);
@@ -170,7 +221,7 @@ __global__ void __launch_bounds__(128, 1) pbs_split_kernel(const cplx* __restric
             if (++stage == NH) { stage = 0; phase ^= 1; }
             const SplitLoadProduct ld{E + lane, E_oth + lane, ring + (size_t)st0 * kHalfCplx + lane,
                                       ring + (size_t)st1 * kHalfCplx + lane, 3 * p, 2 - p};
-            if constexpr (PX) {
+            if constexpr (PX == 1) {
                 cplx* X = X_all + (size_t)p * kSplitXCplx;
                 split_product_send(lane, h, ld, c2, X, w);
                 __syncwarp();
@@ -198,12 +249,12 @@ __global__ void __launch_bounds__(128, 1) pbs_split_kernel(const cplx* __restric
     for (int j = threadIdx.x; j <= kN; j += 128) out[j] = extract_word<AccT>(acc_all, acc_all + 1024, j);
 }
 
-template <typename AccT, int NH, bool PX>
+template <typename AccT, int NH, int PX>
 static void launch_pbs_split_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
                                const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     const size_t smem = (size_t)2 * 1024 * sizeof(pair_t<AccT>) + (size_t)2 * (kSplitECplx + kSplitTCplx) * sizeof(cplx) +
                         (size_t)NH * kHalfCplx * sizeof(cplx) + (size_t)kTabCplx * sizeof(cplx) + 2 * NH * sizeof(uint64_t) +
-                        (PX ? (size_t)2 * kSplitXCplx * sizeof(cplx) : 0);
+                        (PX == 2 ? (size_t)2 * kSplitX2Cplx : PX == 1 ? (size_t)2 * kSplitXCplx : 0) * sizeof(cplx);
     static bool configured = false;
     if (!configured) {
         FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_split_kernel<AccT, NH, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -218,14 +269,16 @@ void launch_pbs_split(int acc_bits, const void* bsk_f, const uint64_t* in_small,
                       const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     if (count <= 0) return;
 #define FSC_SPLIT(ACC, NH, PX) launch_pbs_split_t<ACC, NH, PX>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st)
-    const char* cfg = getenv("FSC_SPLIT_CFG");      // experiment switch: "3r" = three-stage ring + redundant product, "2r", "2x"
+    const char* cfg = getenv("FSC_SPLIT_CFG");      // comparison switch: "3r" = three-stage ring + redundant product, "2r", "22" = rolled step (measured 1-3 % slower); default: split product, unrolled
     if (acc_bits == 32) {
-        if (cfg && cfg[0] == '3') FSC_SPLIT(uint32_t, 3, false);
-        else if (cfg && cfg[0] == '2' && cfg[1] == 'r') FSC_SPLIT(uint32_t, 2, false);
-        else FSC_SPLIT(uint32_t, 2, true);
+        if (cfg && cfg[0] == '3') FSC_SPLIT(uint32_t, 3, 0);
+        else if (cfg && cfg[0] == '2' && cfg[1] == 'r') FSC_SPLIT(uint32_t, 2, 0);
+        else if (cfg && cfg[0] == '2' && cfg[1] == '2') FSC_SPLIT(uint32_t, 2, 2);
+        else FSC_SPLIT(uint32_t, 2, 1);
     } else {
-        if (cfg && cfg[1] == 'r') FSC_SPLIT(uint64_t, 2, false);
-        else FSC_SPLIT(uint64_t, 2, true);
+        if (cfg && cfg[1] == 'r') FSC_SPLIT(uint64_t, 2, 0);
+        else if (cfg && cfg[1] == '2') FSC_SPLIT(uint64_t, 2, 2);
+        else FSC_SPLIT(uint64_t, 2, 1);
     }
 #undef FSC_SPLIT
 }

@@ -24,10 +24,10 @@ struct Tables {
 const Tables& tables() { static Tables T; return T; }
 
 template <typename AccT>
-void blind_rotate(bool px, int n, int base_log, const cplx* bsk_f, const uint64_t* ct, const uint64_t* lut, uint64_t* out) {
+void blind_rotate(int px, int n, int base_log, const cplx* bsk_f, const uint64_t* ct, const uint64_t* lut, uint64_t* out) {
     const Tables& T = tables();
     std::vector<pair_t<AccT>> acc(2 * 1024);
-    std::vector<cplx> E(2 * kSplitECplx), Tb(2 * kSplitTCplx), X(2 * kSplitXCplx);
+    std::vector<cplx> E(2 * kSplitECplx), Tb(2 * kSplitTCplx), X(2 * kSplitXCplx), X2(2 * kSplitX2Cplx);
     static cplx w[2][2][32][16];          // registers of warp (p, h), lane
     const int b = modswitch(ct[n]);
     for (int idx = 0; idx < 1024; ++idx) { acc[idx].x = 0; acc[idx].y = 0; acc[1024 + idx] = lut_pair<AccT>(lut, idx, b); }
@@ -37,14 +37,24 @@ void blind_rotate(bool px, int n, int base_log, const cplx* bsk_f, const uint64_
         const int a = modswitch(ct[i]);
         ALL split_head<AccT>(l, h, acc.data() + p * 1024, a, base_log, E.data() + p * kSplitECplx);
         // barrier
-        ALL split_pass(h, SplitLoadE{E.data() + p * kSplitECplx + l}, StridedConsts{&T.t[0][0][l], 32}, w[p][h][l]);
+        ALL split_pass(h, SplitLoadS{E.data() + p * kSplitECplx + l, 32}, StridedConsts{&T.t[0][0][l], 32}, w[p][h][l]);
         ALL split_xp_store(l, h, Tb.data() + p * kSplitTCplx, w[p][h][l]);
         // barrier
         ALL split_pass(h, SplitLoadT{Tb.data() + p * kSplitTCplx + l * kSplitTRow}, StridedConsts{&T.t[1][0][l], 32}, w[p][h][l]);
         ALL split_spec_store(l, h, E.data() + p * kSplitECplx, w[p][h][l]);
         // barrier
         const cplx* g = bsk_f + (size_t)i * 32 * 4 * 32;
-        if (!px) {      // product by both warps of a polynomial, feeding level 1 directly
+        if (px == 2) {  // run-time-h form of the split product (what the kernel runs): every level-1 output through X2
+            ALL {
+                SplitLoadProduct ld{E.data() + p * kSplitECplx + l, E.data() + (1 - p) * kSplitECplx + l, g + l, g + 16 * 4 * 32 + l, 3 * p, 2 - p};
+                split_product_send2(l, h, ld, StridedConsts{&T.t[2][0][l], 32}, X2.data() + p * kSplitX2Cplx);
+            }
+            // barrier
+            ALL {
+                split_product_recv2(l, h, X2.data() + p * kSplitX2Cplx, w[p][h][l]);
+                split_levels25(h, StridedConsts{&T.t[2][0][l], 32}, w[p][h][l]);
+            }
+        } else if (!px) {      // product by both warps of a polynomial, feeding level 1 directly
             ALL {
                 SplitLoadProduct ld{E.data() + p * kSplitECplx + l, E.data() + (1 - p) * kSplitECplx + l, g + l, g + 16 * 4 * 32 + l, 3 * p, 2 - p};
                 split_pass(h, ld, StridedConsts{&T.t[2][0][l], 32}, w[p][h][l]);
@@ -76,8 +86,8 @@ void emu3_blind_rotate(int acc_bits, int px, int n, int base_log, const double* 
                        const uint64_t* lut, uint64_t* out) {
     const cplx* f = reinterpret_cast<const cplx*>(bsk_f);
     for (int c = 0; c < count; ++c) {
-        if (acc_bits == 64) blind_rotate<uint64_t>(px != 0, n, base_log, f, cts + (size_t)c * (n + 1), lut, out + (size_t)c * (kN + 1));
-        else blind_rotate<uint32_t>(px != 0, n, base_log, f, cts + (size_t)c * (n + 1), lut, out + (size_t)c * (kN + 1));
+        if (acc_bits == 64) blind_rotate<uint64_t>(px, n, base_log, f, cts + (size_t)c * (n + 1), lut, out + (size_t)c * (kN + 1));
+        else blind_rotate<uint32_t>(px, n, base_log, f, cts + (size_t)c * (n + 1), lut, out + (size_t)c * (kN + 1));
     }
 }
 }

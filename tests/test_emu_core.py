@@ -138,12 +138,13 @@ def emu3():
     return E
 
 
-@pytest.mark.parametrize("px", [0, 1])
+@pytest.mark.parametrize("px", [0, 1, 2])
 @pytest.mark.parametrize("acc_bits", [64, 32])
 def test_split_blind_rotation_matches_stream_formulation(emu2, emu3, orc, oracle_keys, rng, acc_bits, px):
     """The half-pass decomposition is the same arithmetic as pass32 on 32 slots up to the order of the product's
     additions: outputs agree with the stream emulator to rounding noise and decrypt like the oracle.
-    px = 1: the Fourier-domain product split between the two warps of a polynomial (what the kernel runs)."""
+    px = 1: the Fourier-domain product split between the two warps of a polynomial; px = 2: the same with the half
+    index at run time (what the kernel runs)."""
     K = oracle_keys("toy")
     n = K.params.lwe_dim
     bf = np.empty(n * 32 * 4 * 32 * 2, dtype=np.float64)
