@@ -193,15 +193,16 @@ def test_error_codes(gpu_ctx, oracle_keys):
     ctx.close()
 
 
-def test_stream_kernel_noise_statistics(oracle_keys, monkeypatch):
-    """the stream kernel forced for every width (FSC_PBS_VARIANT=stream): sigma of fresh PBS outputs over 25 600 real
-    bootstraps of the 2_2 parameter set inside the same budget as the default kernels, zero decode failures."""
+@pytest.mark.parametrize("variant", ["stream", "split"])
+def test_stream_kernel_noise_statistics(oracle_keys, monkeypatch, variant):
+    """the stream kernel, then the split kernel, forced for every width (FSC_PBS_VARIANT): sigma of fresh PBS outputs over
+    25 600 real bootstraps of the 2_2 parameter set inside the same budget as the default kernels, zero decode failures."""
     import fhe_sign_b200 as fsb
-    monkeypatch.setenv("FSC_PBS_VARIANT", "stream")
+    monkeypatch.setenv("FSC_PBS_VARIANT", variant)
     K = oracle_keys("2_2_gaussian")
     ctx = fsb.Context(fsb.Params.preset("2_2_gaussian", acc_bits=32))
     ctx.upload_keys(K.bsk, K.ksk)
-    assert ctx.pbs_kernel_name() == "pbs_stream_kernel"
+    assert ctx.pbs_kernel_name() == "pbs_%s_kernel" % variant
     table = (np.arange(16) * 7 + 3) % 16
     luts = ctx.luts_from_tables(table)
     rng = np.random.default_rng(6)
@@ -214,7 +215,7 @@ def test_stream_kernel_noise_statistics(oracle_keys, monkeypatch):
         e = _noise(K, out, exp)
         sq += float((e * e).sum())
     sigma = (sq / total) ** 0.5
-    print("stream kernel sigma_pbs=2^%.3f over %d bootstraps" % (np.log2(sigma), total))
+    print("%s kernel sigma_pbs=2^%.3f over %d bootstraps" % (variant, np.log2(sigma), total))
     assert fails == 0 and sigma < 2.0**-14.0
     ctx.close()
 
