@@ -219,6 +219,21 @@ def main():
     ms_pbs = ctx.timer_stop() / args.steps
     barrier()
 
+    # latency of one narrow PBS level (at most one ciphertext per SM: the carry-propagation levels of every radix operator)
+    narrow = None
+    if rank == 0:
+        nb = 128
+        dsm_n, dout_n = ctx.lwe(LWE_SMALL, nb), ctx.lwe(LWE_BIG, nb)
+        dsm_n.upload(np.ascontiguousarray(synthetic_batch(nb, n + 1, 0xB201)))
+        ctx.pbs(dsm_n, luts, None, dout_n)
+        ctx.sync()
+        ctx.timer_start()
+        for _ in range(3):
+            ctx.pbs(dsm_n, luts, None, dout_n)
+        narrow = {"blocks": nb, "ms_per_level": ctx.timer_stop() / 3,
+                  "note": "128 independent blocks, one per SM: what a carry-propagation level of a 256-bit operator costs"}
+        dsm_n.free(); dout_n.free()
+
     # ---- end to end through the host-buffer C-ABI call ---------------------------------------
     for _ in range(max(1, min(args.warmup, 2))):
         ctx.apply_lut_host(np_in, luts, lut_idx, out=np_out)
@@ -264,6 +279,7 @@ def main():
                     "h2d_bytes_per_step": int(BATCH * words * 8 + BATCH * 4), "d2h_bytes_per_step": int(BATCH * words * 8)},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "narrow_level": narrow,
         }
         if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only (torchrun pins OMP_NUM_THREADS=1)
             from oracle import orc
