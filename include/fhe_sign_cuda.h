@@ -106,7 +106,10 @@ fsc_status fsc_ks_pbs_batch(fsc_ctx *ctx, const fsc_lwe *in_big, size_t in_first
                             const uint32_t *lut_idx, fsc_lwe *out_big, size_t out_first, size_t count);
 
 /* Host-buffer convenience (the end-to-end call bench.py times as `e2e`): upload `count` big
- * ciphertexts, keyswitch + PBS, download the results.                                            */
+ * ciphertexts, keyswitch + PBS, download the results.  Synchronous: returns when out_big_host is
+ * complete.  Batches of more than one and a half kernel waves are cut at whole waves; uploads and
+ * downloads of neighbouring chunks run on two copy streams beside the bootstraps (pinned host
+ * buffers make the copies asynchronous; pageable ones still work).                               */
 fsc_status fsc_apply_lut_host(fsc_ctx *ctx, const uint64_t *in_big_host, const fsc_luts *luts,
                               const uint32_t *lut_idx, uint64_t *out_big_host, size_t count);
 
