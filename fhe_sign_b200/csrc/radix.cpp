@@ -168,6 +168,70 @@ Radix Evaluator::cast(const Radix& a, int n_blocks) {
 // =======================================================================================
 // carry propagation (parallel prefix over generate / propagate states)
 // =======================================================================================
+// Number of ranks a level of this evaluator may be cut over (1 without level sharding).
+int Evaluator::scan_world() const {
+    const Exchange& x = be_->exchange;
+    return (x.world > 1 && x.all_gather) ? x.world : 1;
+}
+
+// Radix-3 Hillis-Steele scan.  States are re-encoded as the digits of a binary adder, e = 0 (no carry), 1 (propagates),
+// 2 (generates): for three consecutive segments a (most significant), b, c the sum S = 4 e_a + 2 e_b + e_c <= 14 carries
+// out of bit 2 exactly when the joined segment generates (S >= 8) and is all ones exactly when it propagates (S == 7),
+// so ONE lookup joins three segments.  The noise budget (sum of coefficients <= 5 on fresh blocks) forbids the factor 4
+// as a linear coefficient; every position therefore keeps two fresh encodings, Y = 2 e (used with coefficient 2 in its
+// own next join and with coefficient 1 as the middle segment of another) and Z = e (least significant segment, and the
+// final carry-in): S = 2 Y_a + Y_b + Z_c, noise level 4.  Twice the bootstraps of the radix-2 scan per level, log3 n
+// levels instead of log2 n; propagate() takes this path only while a level stays at one ciphertext per SM.
+Radix Evaluator::propagate_radix3(const std::vector<Block>& msg, std::vector<Block>& Y, std::vector<Block>& Z, Block* carry_out) {
+    // msg: clean messages of the n blocks; Y = 2 e, Z = e of the single-block states (propagate()'s first level)
+    const int n = (int)msg.size();
+    const int n_state = (int)Z.size();
+    auto join = [](int S) { return S >= 8 ? 2 : (S == 7 ? 1 : 0); };
+    static const LutTable l_j1 = make_lut([join](int S) { return S <= 14 ? join(S) : 0; });
+    static const LutTable l_j2 = make_lut([join](int S) { return S <= 14 ? 2 * join(S) : 0; });
+    static const LutTable l_final = make_bilut([](int e, int m) { return (m + (e == 2)) & 3; });
+    static const LutTable l_inc = make_lut([](int v) { return (v + 1) & 3; });
+    static const LutTable l_is2 = make_lut([](int v) { return v == 2; });
+    for (int d = 1; d < n_state; d *= 3) {
+        const bool last = 3 * (long)d >= n_state;
+        std::vector<Req> todo;
+        std::vector<std::pair<int, int>> where;
+        std::vector<Block> nY = Y, nZ = Z;
+        for (int i = d; i < n_state; ++i) {
+            Block S = Y[i] * 2 + Y[i - d];
+            if (i - 2 * d >= 0) S = S + Z[i - 2 * d];
+            // Z: least significant segment of a later join, or the final carry-in; Y: any other role in the next level
+            todo.push_back({S, l_j1}); where.emplace_back(1, i);
+            if (!last) { todo.push_back({S, l_j2}); where.emplace_back(0, i); }
+        }
+        std::vector<Block> o = level(todo);
+        for (size_t k = 0; k < o.size(); ++k) (where[k].first ? nZ : nY)[where[k].second] = o[k];
+        Y.swap(nY); Z.swap(nZ);
+    }
+    // final level: add the incoming carry (prefix of the blocks below) to every message
+    Radix res(n);
+    std::vector<Req> todo;
+    std::vector<int> where;
+    if (n > 0) res[0] = msg[0];
+    for (int i = 1; i < n; ++i) {
+        const Block& e = Z[i - 1];
+        if (e.trivial()) {
+            if (e.cst != 2) { res[i] = msg[i]; continue; }
+            todo.push_back({msg[i], l_inc});
+        } else {
+            todo.push_back({e * 4 + msg[i], l_final});
+        }
+        where.push_back(i);
+    }
+    if (carry_out) { todo.push_back({Z[n - 1], l_is2}); where.push_back(-1); }
+    std::vector<Block> o = level(todo);
+    for (size_t k = 0; k < o.size(); ++k) {
+        if (where[k] < 0) *carry_out = o[k];
+        else res[where[k]] = o[k];
+    }
+    return res;
+}
+
 // state: 0 = no carry out, 1 = generates a carry, 2 = propagates an incoming carry
 Radix Evaluator::propagate(const std::vector<Block>& sums, Block* carry_out) {
     const int n = (int)sums.size();
@@ -182,7 +246,13 @@ Radix Evaluator::propagate(const std::vector<Block>& sums, Block* carry_out) {
     // level 1: message and state of every block
     const int n_state = carry_out ? n : n - 1;
     // blocks that are already clean and cannot carry need no bootstrap at all
-    std::vector<Block> msg(n), st(std::max(n_state, 0));
+    // Radix-3 scan for levels that stay within one ciphertext per SM even at two bootstraps per block (2 + log3 n levels
+    // instead of 2 + log2 n): the 16- and 32-block operators on one GPU, everything up to 512 blocks on eight.  A narrow
+    // level costs the same whatever its width, so depth is what counts there.
+    const bool radix3 = n_state > 2 && 2 * (size_t)n_state <= kBlocksPerGpuLevel * (size_t)scan_world();
+    static const LutTable l_s1 = make_lut([](int v) { return v >= 4 ? 2 : (v == 3 ? 1 : 0); });       // block sum -> e
+    static const LutTable l_s2 = make_lut([](int v) { return v >= 4 ? 4 : (v == 3 ? 2 : 0); });       // block sum -> 2 e
+    std::vector<Block> msg(n), st(std::max(n_state, 0)), st2(radix3 ? n_state : 0);
     {
         std::vector<Req> todo;
         std::vector<std::pair<int, int>> where;     // (kind, index)
@@ -191,12 +261,18 @@ Radix Evaluator::propagate(const std::vector<Block>& sums, Block* carry_out) {
             else { todo.push_back({sums[i], lut_msg()}); where.emplace_back(0, i); }
         }
         for (int i = 0; i < n_state; ++i) {
-            if (sums[i].deg <= 2) st[i] = Block::constant(0);
-            else { todo.push_back({sums[i], l_state}); where.emplace_back(1, i); }
+            if (sums[i].deg <= 2) { st[i] = Block::constant(0); if (radix3) st2[i] = Block::constant(0); }
+            else if (!radix3) { todo.push_back({sums[i], l_state}); where.emplace_back(1, i); }
+            else {
+                todo.push_back({sums[i], l_s1}); where.emplace_back(1, i);
+                todo.push_back({sums[i], l_s2}); where.emplace_back(2, i);
+            }
         }
         std::vector<Block> o = level(todo);
-        for (size_t k = 0; k < o.size(); ++k) (where[k].first ? st[where[k].second] : msg[where[k].second]) = o[k];
+        for (size_t k = 0; k < o.size(); ++k)
+            (where[k].first == 0 ? msg[where[k].second] : where[k].first == 1 ? st[where[k].second] : st2[where[k].second]) = o[k];
     }
+    if (radix3) return propagate_radix3(msg, st2, st, carry_out);
     // Hillis-Steele inclusive scan, most significant state dominates unless it propagates
     for (int d = 1; d < n_state; d <<= 1) {
         std::vector<Req> todo;

@@ -29,6 +29,7 @@ constexpr int kMsgBits = 2;
 constexpr int kMsgMod = 4;          // message modulus
 constexpr int kSpace = 16;          // message * carry modulus
 constexpr int kMaxNoise = 5;        // max_noise_level of the parameter set
+constexpr size_t kBlocksPerGpuLevel = 148;   // widest PBS level that still runs at one ciphertext per SM (B200: 148 SMs)
 
 struct RadixError : std::runtime_error {
     using std::runtime_error::runtime_error;
@@ -162,6 +163,8 @@ public:
     // building blocks shared by the operators
     Radix sum_columns(std::vector<std::vector<Block>>& cols);                  // carry-save reduction + propagation
     Radix propagate(const std::vector<Block>& sums, Block* carry_out = nullptr);   // sums[i] <= 7 incl. carry-in
+    Radix propagate_radix3(const std::vector<Block>& msg, std::vector<Block>& Y, std::vector<Block>& Z, Block* carry_out);
+    int scan_world() const;
 
 private:
     RadixBackend* be_;
