@@ -176,3 +176,23 @@ def test_trivial_operands_cost_nothing(M):
     assert M.dec(a + b) == 1311 and M.dec(a * b) == 1234 * 77
     p1, _ = M.api.stats()
     assert p1 == p0
+
+
+@pytest.mark.parametrize("bits,levels", [(8, 3), (32, 5), (64, 6), (256, 9)])
+def test_carry_scan_depth_and_long_carry_chains(M, bits, levels):
+    """The carry scan is radix 3 (propagate_radix3: binary-adder encoding, one lookup joins three segments) while a level
+    of twice the width still runs at one ciphertext per SM — 4-, 16- and 32-block operators on one GPU — and radix 2
+    above (128 blocks: 9 levels).  Longest possible carry chains in both directions, through add and sub."""
+    rnd = random.Random(1000 + bits)
+    n, mask = bits // 2, (1 << bits) - 1
+    cases = [(mask, 1), (mask, mask), (1, mask), (mask - 1, 1), (mask >> 1, 1), (0, 0), (mask ^ (1 << (bits // 2)), 1 << (bits // 2))]
+    cases += [(_rand(rnd, bits), _rand(rnd, bits)) for _ in range(12)]
+    for x, y in cases:
+        a, b = M.enc(x, n), M.enc(y, n)
+        _, l0 = M.api.stats()
+        s = a + b
+        _, l1 = M.api.stats()
+        assert M.dec(s) == (x + y) & mask
+        assert l1 - l0 <= levels
+        assert M.dec(a - b) == (x - y) & mask
+    assert M.counters()["violations"] == 0
