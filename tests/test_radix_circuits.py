@@ -196,3 +196,32 @@ def test_carry_scan_depth_and_long_carry_chains(M, bits, levels):
         assert l1 - l0 <= levels
         assert M.dec(a - b) == (x - y) & mask
     assert M.counters()["violations"] == 0
+
+
+def test_radix3_scan_on_wide_integers_as_an_eight_gpu_node_schedules_them():
+    """With level sharding over 8 ranks the radix-3 scan covers everything up to 592 blocks.  Single process: a
+    world-8 exchange whose threshold is never reached (nothing is actually cut), so only the schedule changes:
+    128 blocks in 2 + 5 levels, 512 blocks in 2 + 6, longest carry chains included."""
+    import ctypes as C
+    from fhe_sign_b200.distributed import EXCHANGE_FN
+    M8 = MockRadix()
+    cb = EXCHANGE_FN(lambda user, buf, nbytes: 0)
+    dummy = (C.c_uint64 * 4)()
+    assert M8.L.fsc_set_level_exchange(M8.ctx, 0, 8, 1 << 30, C.cast(dummy, C.c_void_p), 32, cb, None) == 0
+    rnd = random.Random(88)
+    for bits, levels in ((256, 7), (1024, 8)):
+        n, mask = bits // 2, (1 << bits) - 1
+        cases = [(mask, 1), (mask, mask), (mask >> 1, 1), (mask ^ (1 << (bits // 2)), 1 << (bits // 2))]
+        cases += [(_rand(rnd, bits), _rand(rnd, bits)) for _ in range(6)]
+        for x, y in cases:
+            a, b = M8.enc(x, n), M8.enc(y, n)
+            _, l0 = M8.api.stats()
+            s = a + b
+            _, l1 = M8.api.stats()
+            assert M8.dec(s) == (x + y) & mask
+            assert l1 - l0 <= levels, (bits, l1 - l0)
+            assert M8.dec(a - b) == (x - y) & mask
+    x, y = _rand(rnd, 256), _rand(rnd, 256)
+    assert M8.dec(M8.api.mul_wide(M8.enc(x, 128), M8.enc(y, 128), 256)) == x * y
+    assert M8.counters()["violations"] == 0
+    assert M8.api.sharded_levels() == 0
