@@ -631,38 +631,84 @@ Radix Evaluator::shl(const Radix& a, const Radix& amount) { return barrel(*this,
 // comparisons and selection
 // =======================================================================================
 // per-block ordering code: 0 equal, 1 a < b, 2 a > b; reduced most-significant-first
-Block Evaluator::lt(const Radix& a_in, const Radix& b_in) {
+Block Evaluator::lt(const Radix& a, const Radix& b) {
+    static const LutTable l_is0 = make_lut([](int v) { return v == 0; });
+    return level({{order_code(a, b), l_is0}})[0];
+}
+
+// Ordering code of two radix integers: 0 a < b, 1 equal, 2 a > b.  Reduced most-significant-first by a radix-3 tree:
+// the codes are the digits of a binary adder again (propagate_radix3: "equal" is the transparent digit 1), so one
+// lookup on S = 4 e_a + 2 e_b + e_c joins three segments; in a tree every node has exactly one role in the next level,
+// so it is emitted once, as 2 e (roles a, b) or e (role c, or the root) - same bootstrap count as a binary tree,
+// log3 n levels.
+Block Evaluator::order_code(const Radix& a_in, const Radix& b_in) {
     Radix a = a_in, b = b_in;
     clean(a); clean(b);
     const int n = (int)std::max(a.size(), b.size());
-    if (n == 0) return Block::constant(0);
+    if (n == 0) return Block::constant(1);
     a = cast(a, n); b = cast(b, n);
-    static const LutTable l_cmp = make_bilut([](int x, int y) { return x < y ? 1 : (x > y ? 2 : 0); });
-    static const LutTable l_red = make_bilut([](int hi, int lo) { return hi ? hi : lo; });
-    static const LutTable l_is1 = make_lut([](int v) { return v == 1; });
+    auto cmp = [](int x, int y) { return x < y ? 0 : (x > y ? 2 : 1); };
+    static const LutTable l_cmp1 = make_bilut([cmp](int x, int y) { return cmp(x, y); });
+    static const LutTable l_cmp2 = make_bilut([cmp](int x, int y) { return 2 * cmp(x, y); });
+    auto join3 = [](int S) { return S >= 8 ? 2 : (S == 7 ? 1 : 0); };          // S = 4 e_a + 2 e_b + e_c
+    auto join2 = [](int S) { return S >= 4 ? 2 : (S == 3 ? 1 : 0); };          // S = 2 e_b + e_c
+    static const LutTable l_j31 = make_lut([join3](int S) { return join3(S); });
+    static const LutTable l_j32 = make_lut([join3](int S) { return 2 * join3(S); });
+    static const LutTable l_j21 = make_lut([join2](int S) { return S <= 6 ? join2(S) : 0; });
+    static const LutTable l_j22 = make_lut([join2](int S) { return S <= 6 ? 2 * join2(S) : 0; });
+    // sizes of the tree levels; a node that is alone in its group passes through unchanged, so its encoding is chosen
+    // for the first level in which it has company
+    std::vector<int> sizes{n};
+    while (sizes.back() > 1) sizes.push_back((sizes.back() + 2) / 3);
+    auto doubled = [&](size_t k, int j) {      // does node j of level k have to be emitted as 2 e ?
+        while (k + 1 < sizes.size() && j == sizes[k] - 1 && sizes[k] % 3 == 1) { ++k; j = sizes[k] - 1; }
+        if (sizes[k] == 1) return false;        // the root: plain code
+        return j % 3 != 0;
+    };
     std::vector<Req> reqs;
-    for (int i = 0; i < n; ++i) reqs.push_back({a[i] * 4 + b[i], l_cmp});
+    for (int i = 0; i < n; ++i) reqs.push_back({a[i] * 4 + b[i], doubled(0, i) ? l_cmp2 : l_cmp1});
     std::vector<Block> st = level(reqs);
-    while (st.size() > 1) {
+    for (size_t k = 0; k + 1 < sizes.size(); ++k) {
         reqs.clear();
-        std::vector<Block> nxt;
+        std::vector<Block> nxt((size_t)sizes[k + 1]);
         std::vector<int> where;
-        for (size_t i = 0; i + 1 < st.size(); i += 2) {
-            const Block &lo = st[i], &hi = st[i + 1];
-            if (hi.trivial()) { nxt.push_back(hi.cst ? hi : lo); continue; }
-            if (lo.trivial()) {
-                const int lc = lo.cst;
-                reqs.push_back({hi, make_lut([lc](int v) { return v ? v : lc; })});
-            } else reqs.push_back({hi * 4 + lo, l_red});
-            where.push_back((int)nxt.size());
-            nxt.push_back(Block());
+        for (int g = 0; g < sizes[k + 1]; ++g) {
+            const int lo = 3 * g, cnt = std::min(3, sizes[k] - lo);
+            if (cnt == 1) { nxt[g] = st[lo]; continue; }
+            const bool dbl = doubled(k + 1, g);
+            if (cnt == 2) reqs.push_back({st[lo + 1] + st[lo], dbl ? l_j22 : l_j21});
+            else reqs.push_back({st[lo + 2] * 2 + st[lo + 1] + st[lo], dbl ? l_j32 : l_j31});
+            where.push_back(g);
         }
-        if (st.size() & 1) nxt.push_back(st.back());
         std::vector<Block> o = level(reqs);
-        for (size_t k = 0; k < o.size(); ++k) nxt[where[k]] = o[k];
+        for (size_t q = 0; q < o.size(); ++q) nxt[where[q]] = o[q];
         st.swap(nxt);
     }
-    return level({{st[0], l_is1}})[0];
+    return st[0];
+}
+
+// out = (code == 0, i.e. a < b) ? if_lt : otherwise, the ordering code used directly as the selector (one level less than
+// lt() + select(): min / max of the reference's perf_test.rs:44)
+Radix Evaluator::select_by_order(const Block& code_in, const Radix& lt_in, const Radix& ge_in) {
+    Radix t = lt_in, f = ge_in, c{code_in};
+    clean(t); clean(f); clean(c);
+    const Block& code = c[0];
+    const int n = (int)std::max(t.size(), f.size());
+    t = cast(t, n); f = cast(f, n);
+    static const LutTable l_lt = make_bilut([](int cd, int x) { return cd == 0 ? x : 0; });
+    static const LutTable l_ge = make_bilut([](int cd, int x) { return cd == 0 ? 0 : x; });
+    std::vector<Req> reqs;
+    for (int i = 0; i < n; ++i) {
+        reqs.push_back({code * 4 + t[i], l_lt});
+        reqs.push_back({code * 4 + f[i], l_ge});
+    }
+    std::vector<Block> o = level(reqs);
+    Radix out(n);
+    for (int i = 0; i < n; ++i) {
+        out[i] = o[2 * i] + o[2 * i + 1];
+        out[i].deg = 3;
+    }
+    return out;
 }
 
 Block Evaluator::eq(const Radix& a_in, const Radix& b_in) {
@@ -718,8 +764,8 @@ Radix Evaluator::select(const Block& cond_in, const Radix& t_in, const Radix& f_
     return out;
 }
 
-Radix Evaluator::min(const Radix& a, const Radix& b) { return select(lt(a, b), a, b); }
-Radix Evaluator::max(const Radix& a, const Radix& b) { return select(lt(a, b), b, a); }
+Radix Evaluator::min(const Radix& a, const Radix& b) { return select_by_order(order_code(a, b), a, b); }
+Radix Evaluator::max(const Radix& a, const Radix& b) { return select_by_order(order_code(a, b), b, a); }
 
 // =======================================================================================
 // division by a plaintext constant (Granlund-Montgomery: multiply-high by a magic number)

@@ -150,6 +150,8 @@ public:
     Radix shr(const Radix& a, const Radix& amount);                            // amount taken mod bit width (power of two widths)
     Radix shl(const Radix& a, const Radix& amount);
     Block lt(const Radix& a, const Radix& b);                                  // encrypted bit a < b
+    Block order_code(const Radix& a, const Radix& b);                          // 0 a < b, 1 equal, 2 a > b (radix-3 tree)
+    Radix select_by_order(const Block& code, const Radix& if_lt, const Radix& otherwise);
     Block eq(const Radix& a, const Radix& b);
     Radix select(const Block& cond, const Radix& if_true, const Radix& if_false);
     Radix min(const Radix& a, const Radix& b);

@@ -225,3 +225,26 @@ def test_radix3_scan_on_wide_integers_as_an_eight_gpu_node_schedules_them():
     assert M8.dec(M8.api.mul_wide(M8.enc(x, 128), M8.enc(y, 128), 256)) == x * y
     assert M8.counters()["violations"] == 0
     assert M8.api.sharded_levels() == 0
+
+
+def test_comparison_tree_all_sizes_and_depth(M):
+    """order_code's radix-3 tree (binary-adder encoding of "less / equal / greater", every node emitted once in the form
+    its next role needs, lone nodes passed through): every width from 1 to 40 blocks and a few wide ones, equal and
+    one-bit-apart operands included; min / max select on the code directly (u8 min: 4 levels, 128 blocks: 7)."""
+    rnd = random.Random(4242)
+    for nb in list(range(1, 41)) + [64, 100, 128, 257]:
+        bits = 2 * nb
+        for t in range(6):
+            x = rnd.getrandbits(bits)
+            y = x if t % 3 == 0 else (x ^ (1 << rnd.randrange(bits)) if t % 3 == 1 else rnd.getrandbits(bits))
+            a, b = M.enc(x, nb), M.enc(y, nb)
+            assert M.dec(M.api.lt(a, b)) == (1 if x < y else 0), (nb, x, y)
+            _, l0 = M.api.stats()
+            mn = M.api.min(a, b)
+            _, l1 = M.api.stats()
+            assert M.dec(mn) == min(x, y) and M.dec(M.api.max(a, b)) == max(x, y), (nb, x, y)
+            if nb == 4:
+                assert l1 - l0 <= 4
+            if nb == 128:
+                assert l1 - l0 <= 7
+    assert M.counters()["violations"] == 0
