@@ -240,8 +240,11 @@ Radix Evaluator::propagate(const std::vector<Block>& sums, Block* carry_out) {
     static const LutTable l_final = make_bilut([](int st, int m) { return (m + (st == 1)) & 3; });
     static const LutTable l_inc = make_lut([](int v) { return (v + 1) & 3; });
     static const LutTable l_is1 = make_lut([](int v) { return v == 1; });
-    for (int i = 0; i < n; ++i)
-        if (sums[i].deg > (i == 0 ? 7 : 6)) throw RadixError("propagate: block sum too large for a single carry bit");
+    for (int i = 0; i < n; ++i) {
+        // without a carry out the top block yields a message only: anything that fits the lookup is fine there
+        const int limit = (i == n - 1 && !carry_out) ? (i == 0 ? 15 : 14) : (i == 0 ? 7 : 6);
+        if (sums[i].deg > limit) throw RadixError("propagate: block sum too large for a single carry bit");
+    }
 
     // level 1: message and state of every block
     const int n_state = carry_out ? n : n - 1;
@@ -358,9 +361,18 @@ Radix Evaluator::scalar_add(const Radix& a, const std::vector<uint8_t>& c) {
 // =======================================================================================
 Radix Evaluator::sum_columns(std::vector<std::vector<Block>>& cols) {
     const int n = (int)cols.size();
+    // A column is ready for the carry propagation when its terms add up to at most 6 (7 in column 0, which receives no
+    // carry) within the noise budget of one lookup - however many terms that is: the propagation's first level reads the
+    // sum directly.  (Asking for at most two terms costs whole levels of one or two bootstraps at the end of narrow
+    // products.)
     auto needs_round = [&]() {
-        for (const auto& c : cols)
-            if (c.size() > 2) return true;
+        for (int c = 0; c < n; ++c) {
+            int deg = 0, nl = 0;
+            for (const auto& b : cols[c]) { deg += b.deg; nl += b.nl; }
+            // the most significant column wraps: no state is derived from it, only its message (any sum below 15 + carry-in)
+            const int limit = c == n - 1 ? (c == 0 ? 15 : 14) : (c == 0 ? 7 : 6);
+            if (deg > limit || nl > kMaxNoise) return true;
+        }
         return false;
     };
     while (needs_round()) {
