@@ -815,14 +815,20 @@ void sub_in_place(Nat& a, const Nat& b) {     // a >= b
         borrow = v < 0; a.bit[i] = (uint8_t)(v & 1);
     }
 }
-Nat divide(const Nat& num, const Nat& den) {  // floor(num / den), schoolbook binary long division
+Nat divide(const Nat& num, const Nat& den, Nat* rem = nullptr) {  // floor(num / den), schoolbook binary long division
     Nat q(num.bit.size()), r(num.bit.size() + 1);
     for (int i = (int)num.bit.size() - 1; i >= 0; --i) {
         for (int j = (int)r.bit.size() - 1; j > 0; --j) r.bit[j] = r.bit[j - 1];
         r.bit[0] = num.bit[i];
         if (cmp(r, den) >= 0) { sub_in_place(r, den); q.bit[i] = 1; }
     }
+    if (rem) *rem = r;
     return q;
+}
+void increment(Nat& m) {
+    size_t i = 0;
+    while (i < m.bit.size() && m.bit[i]) { m.bit[i] = 0; ++i; }
+    if (i == m.bit.size()) m.bit.push_back(1); else m.bit[i] = 1;
 }
 }  // namespace
 
@@ -843,27 +849,44 @@ Radix Evaluator::scalar_div(const Radix& a, const std::vector<uint8_t>& d_digits
         q = scalar_shr(a, (unsigned)top);
     } else {
         const int l = top + 1;                   // ceil(log2 d) for non powers of two
-        // m' = floor(2^W (2^l - d) / d) + 1, fits W bits
-        Nat num((size_t)W + l + 1);
-        {
-            Nat t((size_t)l + 1);
-            t.bit[l] = 1;
-            sub_in_place(t, d);                  // 2^l - d
-            for (int i = 0; i <= l; ++i) if (t.bit[i]) num.bit[i + W] = 1;
+        // Round-up method: M_s = ceil(2^(W+s) / d) divides exactly for every W-bit dividend as soon as its excess
+        // e = M_s d - 2^(W+s) is at most 2^s.  If such an M_s still fits W bits, floor(a / d) = mulhi(a, M_s) >> s with
+        // no fix-up at all (d = 5: M = 0xCC...CD, s = 2): one product and a shift instead of product, subtraction,
+        // shift, addition, shift - 10 PBS levels instead of 21 for the reference's `x / 5` (perf_test.rs:54).
+        int s_fit = -1;
+        Nat m_fit;
+        for (int sft = 0; sft <= l && s_fit < 0; ++sft) {
+            Nat num((size_t)W + sft + 1);
+            num.bit[W + sft] = 1;
+            Nat r;
+            Nat m = divide(num, d, &r);
+            Nat e(d.bit.size() + 1);                 // excess of the rounded-up multiplier: d - r (0 if d divides)
+            if (!r.zero()) { e = Nat(d.bit.size() + 1); for (size_t i = 0; i < d.bit.size(); ++i) e.bit[i] = d.bit[i]; sub_in_place(e, r); increment(m); }
+            Nat lim((size_t)sft + 1);
+            lim.bit[sft] = 1;                        // 2^s
+            if (cmp(e, lim) <= 0 && m.top() < W) { s_fit = sft; m_fit = m; }
         }
-        Nat m = divide(num, d);
-        {   // + 1
-            size_t i = 0;
-            while (i < m.bit.size() && m.bit[i]) { m.bit[i] = 0; ++i; }
-            if (i == m.bit.size()) m.bit.push_back(1); else m.bit[i] = 1;
+        if (s_fit >= 0) {
+            Radix wide = scalar_mul(cast(a, 2 * n), m_fit.to_digits(n), 2 * n);      // full 2W-bit product
+            Radix t1(wide.begin() + n, wide.end());                               // mulhi
+            q = scalar_shr(t1, (unsigned)s_fit);
+        } else {
+            // the multiplier needs W + 1 bits, M = 2^W + m': floor(a / d) = (mulhi(a, m') + a) >> l, the sum taken one
+            // block wider instead of the register-width dance (a - t) / 2 + t
+            Nat num((size_t)W + l + 1);
+            {
+                Nat t((size_t)l + 1);
+                t.bit[l] = 1;
+                sub_in_place(t, d);                  // 2^l - d
+                for (int i = 0; i <= l; ++i) if (t.bit[i]) num.bit[i + W] = 1;
+            }
+            Nat m = divide(num, d);                  // m' = floor(2^W (2^l - d) / d) + 1, fits W bits
+            increment(m);
+            Radix wide = scalar_mul(cast(a, 2 * n), m.to_digits(n), 2 * n);
+            Radix t1(wide.begin() + n, wide.end());
+            Radix sum = add(cast(t1, n + 1), cast(a, n + 1));
+            q = cast(scalar_shr(sum, (unsigned)l), n);
         }
-        const std::vector<uint8_t> mdig = m.to_digits(n);
-        Radix wide = scalar_mul(cast(a, 2 * n), mdig, 2 * n);        // full 2W-bit product
-        Radix t1(wide.begin() + n, wide.end());                      // mulhi
-        Radix diff = sub(a, t1);
-        Radix half = scalar_shr(diff, 1);
-        Radix s = add(half, t1);
-        q = scalar_shr(s, (unsigned)(l - 1));
     }
     if (rem) {
         Radix qd = scalar_mul(q, d.to_digits(n), n);
