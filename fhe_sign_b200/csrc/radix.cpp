@@ -472,6 +472,11 @@ Radix Evaluator::mul(const Radix& a_in, const Radix& b_in, int out_blocks) {
 }
 
 Radix Evaluator::scalar_mul(const Radix& a_in, const std::vector<uint8_t>& c, int out_blocks) {
+    return scalar_mul_add(a_in, c, nullptr, out_blocks);
+}
+
+// a * c + addend in one column sum and one carry propagation (addend: clean blocks, may be null)
+Radix Evaluator::scalar_mul_add(const Radix& a_in, const std::vector<uint8_t>& c, const Radix* addend, int out_blocks) {
     Radix a = a_in;
     clean(a);
     const int n = out_blocks < 0 ? (int)a.size() : out_blocks;
@@ -501,6 +506,11 @@ Radix Evaluator::scalar_mul(const Radix& a_in, const std::vector<uint8_t>& c, in
             if (d == 1) push(i + j, a[i]);
             else { push(i + j, lo[d][i]); push(i + j + 1, hi[d][i]); }
         }
+    }
+    if (addend) {
+        Radix ad = *addend;
+        clean(ad);
+        for (int i = 0; i < (int)ad.size(); ++i) push(i, ad[i]);
     }
     return sum_columns(cols);
 }
@@ -825,6 +835,32 @@ Nat divide(const Nat& num, const Nat& den, Nat* rem = nullptr) {  // floor(num /
     if (rem) *rem = r;
     return q;
 }
+Nat multiply(const Nat& a, const Nat& b) {
+    Nat r(a.bit.size() + b.bit.size() + 1);
+    for (size_t i = 0; i < a.bit.size(); ++i) {
+        if (!a.bit[i]) continue;
+        int carry = 0;
+        for (size_t j = 0; j < b.bit.size() || carry; ++j) {
+            const int v = r.bit[i + j] + (j < b.bit.size() ? b.bit[j] : 0) + carry;
+            r.bit[i + j] = (uint8_t)(v & 1); carry = v >> 1;
+        }
+    }
+    return r;
+}
+Nat nat_add(const Nat& a, const Nat& b) {
+    Nat r(std::max(a.bit.size(), b.bit.size()) + 1);
+    int carry = 0;
+    for (size_t i = 0; i < r.bit.size(); ++i) {
+        const int v = (i < a.bit.size() ? a.bit[i] : 0) + (i < b.bit.size() ? b.bit[i] : 0) + carry;
+        r.bit[i] = (uint8_t)(v & 1); carry = v >> 1;
+    }
+    return r;
+}
+Nat shift_right(const Nat& a, size_t k) {
+    Nat r(a.bit.size() > k ? a.bit.size() - k : 0);
+    for (size_t i = 0; i < r.bit.size(); ++i) r.bit[i] = a.bit[i + k];
+    return r;
+}
 void increment(Nat& m) {
     size_t i = 0;
     while (i < m.bit.size() && m.bit[i]) { m.bit[i] = 0; ++i; }
@@ -895,10 +931,61 @@ Radix Evaluator::scalar_div(const Radix& a, const std::vector<uint8_t>& d_digits
     return q;
 }
 
-Radix Evaluator::scalar_rem(const Radix& a, const std::vector<uint8_t>& d) {
-    Radix r;
-    scalar_div(a, d, &r);
-    return r;
+// a mod d.  Moduli of the form 2^k - c with a small c (the secp256k1 group order of the reference's scalar.rs:8 is
+// 2^256 - c, c < 2^129) are reduced by folding, hi 2^k + lo = hi c + lo (mod d): each fold is one multiplication by the
+// constant c with the low part riding in the same column sum, the value shrinks by about k - bits(c) bits per fold, and
+// once it is provably below 2 d one conditional subtraction finishes.  A 514-bit value takes three folds (258-, 132- and
+// 6-bit high parts) instead of the two 257-block products of the general quotient-and-multiply-back path.
+Radix Evaluator::scalar_rem(const Radix& a, const std::vector<uint8_t>& d_digits) {
+    const Nat d = Nat::from_digits(d_digits);
+    if (d.zero()) throw RadixError("division by zero");
+    const int k = d.top() + 1;
+    Nat c((size_t)k + 1);
+    c.bit[k] = 1;
+    sub_in_place(c, d);                              // 2^k - d
+    const int cbits = c.top() + 1;
+    bool foldable = (k % 2 == 0) && cbits > 0 && cbits <= k / 2 + 1 && 2 * (int)a.size() > k;
+    if (foldable) {      // dry run on the bounds: the folds must bring the value below 2 d within a few rounds
+        Nat ub0(2 * a.size());
+        for (auto& b : ub0.bit) b = 1;
+        Nat ones((size_t)k);
+        for (auto& b : ones.bit) b = 1;
+        const Nat dd = nat_add(d, d);
+        int rounds = 0;
+        while (cmp(ub0, dd) >= 0 && rounds <= 8) { ub0 = nat_add(ones, multiply(shift_right(ub0, (size_t)k), c)); ++rounds; }
+        foldable = cmp(ub0, dd) < 0;
+    }
+    if (!foldable) {
+        Radix r;
+        scalar_div(a, d_digits, &r);
+        return r;
+    }
+    const int kb = k / 2;                            // blocks below 2^k
+    const std::vector<uint8_t> cdig = c.to_digits((size_t)(cbits + 1) / 2);
+    Nat two_d = nat_add(d, d);
+    Nat ub(2 * a.size());
+    for (auto& b : ub.bit) b = 1;                    // upper bound of the running value
+    Nat low_ones((size_t)k);
+    for (auto& b : low_ones.bit) b = 1;              // 2^k - 1
+    Radix r = a;
+    for (int guard = 0; cmp(ub, two_d) >= 0; ++guard) {
+        if (guard > 16) throw RadixError("scalar_rem: fold did not converge");
+        const Nat hi_ub = shift_right(ub, (size_t)k);
+        Nat nub = nat_add(low_ones, multiply(hi_ub, c));
+        const int out_blocks = (nub.top() + 2) / 2;
+        Radix lo(r.begin(), r.begin() + std::min<size_t>(kb, r.size()));
+        Radix hi(r.size() > (size_t)kb ? r.begin() + kb : r.end(), r.end());
+        hi.resize(std::min<size_t>(hi.size(), (size_t)(hi_ub.top() + 2) / 2), Block::constant(0));   // blocks above the bound are zero
+        r = scalar_mul_add(hi, cdig, &lo, out_blocks);
+        ub = nub;
+    }
+    if (cmp(ub, d) >= 0) {                           // r < 2 d: subtract d where that does not borrow
+        const int w = (int)r.size();
+        Block not_borrow;
+        Radix t = sub(r, trivial_big(d.to_digits((size_t)w)), &not_borrow);
+        r = select(not_borrow, t, r);
+    }
+    return cast(r, (int)a.size());
 }
 
 }  // namespace fsc

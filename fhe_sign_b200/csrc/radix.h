@@ -143,6 +143,7 @@ public:
     Radix scalar_add(const Radix& a, const std::vector<uint8_t>& c);
     Radix mul(const Radix& a, const Radix& b, int out_blocks = -1);           // wrapping at out_blocks (default |a|)
     Radix scalar_mul(const Radix& a, const std::vector<uint8_t>& c, int out_blocks = -1);
+    Radix scalar_mul_add(const Radix& a, const std::vector<uint8_t>& c, const Radix* addend, int out_blocks);
     Radix scalar_shr(const Radix& a, unsigned bits);
     Radix scalar_shl(const Radix& a, unsigned bits);
     Radix scalar_and(const Radix& a, const std::vector<uint8_t>& mask);

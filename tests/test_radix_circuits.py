@@ -248,3 +248,25 @@ def test_comparison_tree_all_sizes_and_depth(M):
             if nb == 128:
                 assert l1 - l0 <= 7
     assert M.counters()["violations"] == 0
+
+
+def test_rem_by_pseudo_mersenne_moduli_folds(M):
+    """scalar_rem folds hi 2^k + lo -> hi c + lo for moduli 2^k - c with a small c (secp256k1's group order n and field
+    prime p, 2^64 - 59, ...): edge values around multiples of the modulus, and the cost of the reference's missing
+    `mod n` step (514-bit value, scalar.rs:8) stays far below the general quotient-and-multiply-back path (75 k PBS)."""
+    rnd = random.Random(606)
+    n_order = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+    p_field = 2**256 - 2**32 - 977
+    for d, nb in ((n_order, 257), (n_order, 129), (p_field, 256), (2**64 - 59, 64), (2**32 - 5, 32), (2**16 - 15, 16)):
+        bits = 2 * nb
+        vals = [(1 << bits) - 1, d, d - 1, d + 1, 2 * d - 1, 2 * d, 0, d * ((1 << bits) // d), d * ((1 << bits) // d) - 1]
+        vals += [rnd.getrandbits(bits) for _ in range(3)]
+        for v in vals:
+            v %= 1 << bits
+            p0, _ = M.api.stats()
+            r = M.enc(v, nb) % d
+            p1, _ = M.api.stats()
+            assert M.dec(r) == v % d, (hex(d), hex(v))
+            if nb == 257:
+                assert p1 - p0 < 20000
+    assert M.counters()["violations"] == 0
