@@ -167,6 +167,7 @@ class BigUintFHE:
             return k + BigUintFHE([], k.client_key)
         n_prod = len(e.digits) + len(d.digits)
         n_out = max(len(k.digits), n_prod) + 1                               # Add appends the final carry digit
-        prod = api.mul_wide(e._as_radix(), d._as_radix(), BLOCKS_U32 * n_prod)
-        total = api.sum([api.cast(prod, BLOCKS_U32 * n_out), api.cast(k._as_radix(), BLOCKS_U32 * n_out)], BLOCKS_U32 * n_out)
+        # the addend joins the product's column sum: one carry propagation for both (e*d < 2^(32 n_prod), so nothing is lost
+        # by forming the sum at n_out digits directly)
+        total = api.mul_add_wide(e._as_radix(), d._as_radix(), k._as_radix(), BLOCKS_U32 * n_out)
         return BigUintFHE._from_radix(total, n_out, k.client_key)

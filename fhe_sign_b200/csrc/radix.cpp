@@ -436,6 +436,12 @@ Radix Evaluator::sum(const std::vector<Radix>& operands, int n_blocks) {
 // multiplication
 // =======================================================================================
 Radix Evaluator::mul(const Radix& a_in, const Radix& b_in, int out_blocks) {
+    return mul_add(a_in, b_in, nullptr, out_blocks);
+}
+
+// a * b + addend with the addend's blocks riding in the product's column sum: one carry propagation for both
+// (the reference's `k + (e * d)`, src/schnorr.rs:274)
+Radix Evaluator::mul_add(const Radix& a_in, const Radix& b_in, const Radix* addend, int out_blocks) {
     Radix a = a_in, b = b_in;
     clean(a); clean(b);
     const int n = out_blocks < 0 ? (int)a.size() : out_blocks;
@@ -468,6 +474,12 @@ Radix Evaluator::mul(const Radix& a_in, const Radix& b_in, int out_blocks) {
     }
     std::vector<Block> o = level(reqs);
     for (size_t k = 0; k < o.size(); ++k) cols[dest[k]].push_back(o[k]);
+    if (addend) {
+        Radix ad = *addend;
+        clean(ad);
+        for (int i = 0; i < (int)ad.size() && i < n; ++i)
+            if (!(ad[i].trivial() && ad[i].cst == 0)) cols[i].push_back(ad[i]);
+    }
     return sum_columns(cols);
 }
 

@@ -142,6 +142,7 @@ public:
     Radix sub(const Radix& a, const Radix& b, Block* not_borrow = nullptr);
     Radix scalar_add(const Radix& a, const std::vector<uint8_t>& c);
     Radix mul(const Radix& a, const Radix& b, int out_blocks = -1);           // wrapping at out_blocks (default |a|)
+    Radix mul_add(const Radix& a, const Radix& b, const Radix* addend, int out_blocks);   // a * b + addend, one propagation
     Radix scalar_mul(const Radix& a, const std::vector<uint8_t>& c, int out_blocks = -1);
     Radix scalar_mul_add(const Radix& a, const std::vector<uint8_t>& c, const Radix* addend, int out_blocks);
     Radix scalar_shr(const Radix& a, unsigned bits);

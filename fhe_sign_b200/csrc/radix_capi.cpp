@@ -158,6 +158,14 @@ fsc_status fsc_radix_mul_wide(fsc_ctx* ctx, const fsc_radix* a, const fsc_radix*
     RX_END(ctx)
 }
 
+fsc_status fsc_radix_mul_add_wide(fsc_ctx* ctx, const fsc_radix* a, const fsc_radix* b, const fsc_radix* addend, size_t out_blocks,
+                                  fsc_radix** out) {
+    RX_BEGIN(ctx)
+    need(a && b && addend && out, "null argument");
+    emit(ctx, out, ctx->ev->mul_add(a->blocks, b->blocks, &addend->blocks, (int)out_blocks));
+    RX_END(ctx)
+}
+
 fsc_status fsc_radix_cast(fsc_ctx* ctx, const fsc_radix* a, size_t n_blocks, fsc_radix** out) {
     RX_BEGIN(ctx)
     need(a && out, "null argument");

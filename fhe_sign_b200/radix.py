@@ -10,7 +10,7 @@ OPS = dict(add=0, sub=1, mul=2, min=3, max=4, shr=5, shl=6, and_=7, or_=8, xor=9
 WORDS = 2049
 
 RADIX_EXPORTS = ["fsc_radix_from_lwe", "fsc_radix_to_lwe", "fsc_radix_trivial", "fsc_radix_clone", "fsc_radix_free",
-                 "fsc_radix_len", "fsc_radix_binary", "fsc_radix_scalar", "fsc_radix_mul_wide", "fsc_radix_cast",
+                 "fsc_radix_len", "fsc_radix_binary", "fsc_radix_scalar", "fsc_radix_mul_wide", "fsc_radix_mul_add_wide", "fsc_radix_cast",
                  "fsc_radix_slice", "fsc_radix_concat", "fsc_radix_sum", "fsc_radix_select", "fsc_radix_stats",
                  "fsc_radix_stats2", "fsc_set_level_exchange"]
 
@@ -23,6 +23,7 @@ def declare(L):
         "fsc_radix_trivial": [vp, vp, sz, sz, pp], "fsc_radix_clone": [vp, vp, pp], "fsc_radix_free": [vp, vp],
         "fsc_radix_len": [vp, C.POINTER(sz)], "fsc_radix_binary": [vp, u32, vp, vp, pp],
         "fsc_radix_scalar": [vp, u32, vp, vp, sz, pp], "fsc_radix_mul_wide": [vp, vp, vp, sz, pp],
+        "fsc_radix_mul_add_wide": [vp, vp, vp, vp, sz, pp],
         "fsc_radix_cast": [vp, vp, sz, pp], "fsc_radix_slice": [vp, vp, sz, sz, pp],
         "fsc_radix_concat": [vp, vp, sz, pp], "fsc_radix_sum": [vp, vp, sz, sz, pp],
         "fsc_radix_select": [vp, vp, vp, vp, pp], "fsc_radix_stats": [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
@@ -106,6 +107,10 @@ class RadixApi:
 
     def mul_wide(self, a, b, out_blocks):
         return self._new(self.L.fsc_radix_mul_wide, a.h, b.h, out_blocks)
+
+    def mul_add_wide(self, a, b, addend, out_blocks):
+        """a * b + addend with one carry propagation (the addend joins the product's column sum)."""
+        return self._new(self.L.fsc_radix_mul_add_wide, a.h, b.h, addend.h, out_blocks)
 
     def cast(self, a, n_blocks):
         return self._new(self.L.fsc_radix_cast, a.h, n_blocks)

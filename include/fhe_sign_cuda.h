@@ -155,6 +155,10 @@ fsc_status fsc_radix_binary(fsc_ctx *ctx, uint32_t op, const fsc_radix *a, const
 fsc_status fsc_radix_scalar(fsc_ctx *ctx, uint32_t op, const fsc_radix *a, const uint8_t *scalar_le, size_t n_bytes, fsc_radix **out);
 /* a * b without wrapping at |a| blocks: out_blocks result blocks (e.g. 256 for a 256x256-bit product). */
 fsc_status fsc_radix_mul_wide(fsc_ctx *ctx, const fsc_radix *a, const fsc_radix *b, size_t out_blocks, fsc_radix **out);
+/* a * b + addend, out_blocks result blocks: the addend rides in the product's column sum, one carry propagation for
+ * both - the fused form of `k_fhe + (e_fhe * privkey_fhe)` (src/schnorr.rs:274).                  */
+fsc_status fsc_radix_mul_add_wide(fsc_ctx *ctx, const fsc_radix *a, const fsc_radix *b, const fsc_radix *addend,
+                                  size_t out_blocks, fsc_radix **out);
 /* FheUintM::cast_from (src/biguint.rs:110,116,135-137): truncate or zero-extend; no device work.  */
 fsc_status fsc_radix_cast(fsc_ctx *ctx, const fsc_radix *a, size_t n_blocks, fsc_radix **out);
 fsc_status fsc_radix_slice(fsc_ctx *ctx, const fsc_radix *a, size_t first, size_t n_blocks, fsc_radix **out);

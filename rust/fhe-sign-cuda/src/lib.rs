@@ -39,6 +39,9 @@ pub mod sys {
         pub fn fsc_radix_binary(ctx: *mut fsc_ctx, op: u32, a: *const fsc_radix, b: *const fsc_radix, out: *mut *mut fsc_radix) -> i32;
         pub fn fsc_radix_scalar(ctx: *mut fsc_ctx, op: u32, a: *const fsc_radix, s: *const u8, n_bytes: usize, out: *mut *mut fsc_radix) -> i32;
         pub fn fsc_radix_cast(ctx: *mut fsc_ctx, a: *const fsc_radix, n_blocks: usize, out: *mut *mut fsc_radix) -> i32;
+        // fused schedule: a * b without wrapping, and a * b + addend with one carry propagation
+        pub fn fsc_radix_mul_wide(ctx: *mut fsc_ctx, a: *const fsc_radix, b: *const fsc_radix, out_blocks: usize, out: *mut *mut fsc_radix) -> i32;
+        pub fn fsc_radix_mul_add_wide(ctx: *mut fsc_ctx, a: *const fsc_radix, b: *const fsc_radix, addend: *const fsc_radix, out_blocks: usize, out: *mut *mut fsc_radix) -> i32;
         // on-disk formats (csrc/keyfile.cpp): expanded server key written by the signer's side, read by the GPU host
         pub fn fsc_server_keys_load(path: *const c_char, params: *mut fsc_params, bsk: *mut *mut u64, bsk_words: *mut usize,
                                     ksk: *mut *mut u64, ksk_words: *mut usize) -> i32;

@@ -43,7 +43,7 @@ def main():
     ops = [
         ("256-bit mul (wrapping)", lambda: a * b, (x * y) % 2**256),
         ("256-bit shr by encrypted amount", lambda: a >> b, x >> (y % 256)),
-        ("k + e*d fused, 256x256+256", lambda: R.sum([R.mul_wide(a, b, 256), R.cast(c, 272)], 272), x * y + z),
+        ("k + e*d fused, 256x256+256", lambda: R.mul_add_wide(a, b, c, 272), x * y + z),
         ("256-bit div 5", lambda: a // 5, x // 5),
         ("514-bit rem n", lambda: w % N_ORDER, (x * y + z) % N_ORDER),
     ]

@@ -47,7 +47,7 @@ def main():
         ("256-bit shr by scalar 77", lambda: a256 >> 77),
         ("256-bit shr by encrypted amount", lambda: a256 >> b256),
         ("256x256->512-bit mul (mul_wide)", lambda: R.mul_wide(a256, b256, 256)),
-        ("k + e*d fused (schnorr.rs:274)", lambda: R.sum([R.mul_wide(a256, b256, 256), R.cast(c256, 272)], 272)),
+        ("k + e*d fused (schnorr.rs:274)", lambda: R.mul_add_wide(a256, b256, c256, 272)),
         ("256-bit div 5", lambda: a256 // 5),
         ("514-bit rem n (secp256k1 order)", lambda: a513 % N_ORDER),
     ]
