@@ -171,3 +171,13 @@ class BigUintFHE:
         # by forming the sum at n_out digits directly)
         total = api.mul_add_wide(e._as_radix(), d._as_radix(), k._as_radix(), BLOCKS_U32 * n_out)
         return BigUintFHE._from_radix(total, n_out, k.client_key)
+
+    def rem_scalar(self, modulus):
+        """self mod a plaintext modulus, homomorphically (the reference takes `% n` after decryption,
+        src/schnorr.rs:276).  Digits follow the modulus' width."""
+        api = _api()
+        if not self.digits:
+            return BigUintFHE([], self.client_key)
+        n_digits = max(1, (int(modulus).bit_length() + 31) // 32)
+        r = api.scalar("rem", self._as_radix(), int(modulus))
+        return BigUintFHE._from_radix(r, min(n_digits, len(self.digits)), self.client_key)

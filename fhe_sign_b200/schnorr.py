@@ -64,10 +64,11 @@ class Signature:
         return _b32(self.r_x) + _b32(self.s)
 
 
-def sign_fhe_with_k0(message, k0, privkey, privkey_fhe, client_key, fused=False):
+def sign_fhe_with_k0(message, k0, privkey, privkey_fhe, client_key, fused=False, reduce_encrypted=False):
     """src/schnorr.rs:235-290.  `privkey` is the plaintext key (used only for the public key, :241);
     `privkey_fhe` is its BigUintFHE encryption.  fused=True evaluates the same expression with the
-    batched schedule (BigUintFHE.mul_add_fused)."""
+    batched schedule (BigUintFHE.mul_add_fused).  reduce_encrypted=True also takes `mod n` under encryption
+    (SURVEY.md 8f.2), so that only the 256-bit s is ever decrypted; the reference reduces in plaintext (:276)."""
     pubkey = get_public_key_with_even_y(privkey)
     r = _mul(k0)
     k = N - k0 if r[1] % 2 == 1 else k0
@@ -78,5 +79,7 @@ def sign_fhe_with_k0(message, k0, privkey, privkey_fhe, client_key, fused=False)
         s_fhe = BigUintFHE.mul_add_fused(k_fhe, e_fhe, privkey_fhe.clone())
     else:
         s_fhe = k_fhe + (e_fhe * privkey_fhe.clone())
+    if reduce_encrypted:
+        s_fhe = s_fhe.rem_scalar(N)
     s_without_mod = s_fhe.to_biguint(client_key)
     return Signature(r[0], s_without_mod % N)

@@ -99,3 +99,14 @@ def test_sign_fhe_with_k0_all_vectors(ck, fused):
         sig = schnorr.sign_fhe_with_k0(msg, k0, d, BigUintFHE.new(d, ck), ck, fused=fused)
         assert sig.to_bytes().hex().upper() == v["reference_signature"]
         assert sig.to_bytes() == sm.sign_with_k0(msg, k0, d)
+
+
+def test_sign_with_the_reduction_under_encryption(ck):
+    """`s = (k + e d) mod n` entirely under encryption (folding reduction by the secp256k1 order), then the
+    same signature bytes as the reference's plaintext `% n` (src/schnorr.rs:276)."""
+    for v in GOLDEN[:3]:
+        d, k0, msg = int(v["secret_key"], 16), int(v["k0"], 16), bytes.fromhex(v["message"])
+        sig = schnorr.sign_fhe_with_k0(msg, k0, d, BigUintFHE.new(d, ck), ck, fused=True, reduce_encrypted=True)
+        assert sig.to_bytes().hex().upper() == v["reference_signature"]
+    x = BigUintFHE.new(sm.N * 5 + 12345, ck) if hasattr(sm, "N") else BigUintFHE.new(schnorr.N * 5 + 12345, ck)
+    assert x.rem_scalar(schnorr.N).to_biguint(ck) == 12345
