@@ -97,3 +97,19 @@ def test_256_bit_mul_add(cl):
     prod = cl.api.mul_wide(a, b, 256)
     s = cl.api.sum([prod, cl.api.cast(c, 257)], 257)
     assert cl.dec(s) == x * y + z
+
+
+def test_k_plus_ed_fused_and_reduced_mod_n(cl):
+    """src/schnorr.rs:272-276 end to end on ciphertexts: k + e*d as one fsc_radix_mul_add_wide (the addend in the
+    product's column sum), then `mod n` under encryption by the folding reduction - the reference
+    takes it after decryption.  Also x / 5 and x % (2^32 - 5) through the fix-up-free division and the fold."""
+    n_order = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+    rnd = random.Random(13)
+    k, e, d = rnd.getrandbits(256) % n_order, rnd.getrandbits(256), rnd.getrandbits(256) % n_order
+    s = cl.api.mul_add_wide(cl.enc(e, 128), cl.enc(d, 128), cl.enc(k, 128), 257)
+    assert cl.dec(s) == k + e * d
+    assert cl.dec(s % n_order) == (k + e * d) % n_order
+    x = rnd.getrandbits(32)
+    a = cl.enc(x, 16)
+    assert cl.dec(a // 5) == x // 5
+    assert cl.dec(a % (2**32 - 5)) == x % (2**32 - 5)
