@@ -9,9 +9,15 @@
 // file touches ciphertext words: blocks are symbolic linear combinations of device slots, so
 // additions, scalar multiplications, casts, block shifts and trivial constants cost no device work.
 //
-// The circuits are this engine's own (carry propagation by parallel prefix, schoolbook partial
-// products + carry-save column sums, barrel shifter, magic-number scalar division); only decrypted
-// results are contractual.
+// The circuits are this engine's own; only decrypted results are contractual:
+//   * carry propagation by parallel prefix - radix 2, or radix 3 (states as binary-adder digits, one lookup joins three
+//     segments) wherever twice the bootstraps still fit one ciphertext per SM per GPU: a narrow level costs the same
+//     whatever its width, so depth is what counts there;
+//   * schoolbook partial products + carry-save column sums (an addend may ride in the sum: mul_add) + one propagation;
+//   * comparison by a radix-3 tree of ordering codes, min / max selecting on the code directly;
+//   * barrel shifter for encrypted amounts;
+//   * division by a constant through a rounded-up magic multiplier (no fix-up when it fits the register width);
+//   * remainder by 2^k - c with small c (the secp256k1 order) by folding hi 2^k + lo -> hi c + lo.
 #pragma once
 #include <stdint.h>
 
