@@ -1,6 +1,8 @@
 // radix.cpp — radix-integer operators as sequences of batched PBS levels (see radix.h).
 #include "radix.h"
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <functional>
 
@@ -9,6 +11,11 @@ namespace fsc {
 // =======================================================================================
 // symbolic block arithmetic
 // =======================================================================================
+bool noise_in_variance_units() {
+    static const bool v = [] { const char* e = getenv("FSC_RADIX_NOISE"); return e && e[0] == 'v'; }();
+    return v;
+}
+
 static void merge_term(std::vector<std::pair<SlotP, int32_t>>& t, const SlotP& s, int32_t c) {
     if (c == 0) return;
     for (auto& e : t)
@@ -24,7 +31,7 @@ Block operator+(const Block& a, const Block& b) {
     Block r = a;
     for (const auto& e : b.terms) merge_term(r.terms, e.first, e.second);
     drop_zero_terms(r);
-    r.cst += b.cst; r.deg += b.deg; r.nl += b.nl;
+    r.cst += b.cst; r.deg += b.deg; r.nl += b.nl; r.nv += b.nv;
     return r;
 }
 Block operator*(const Block& a, int c) {
@@ -32,7 +39,7 @@ Block operator*(const Block& a, int c) {
     Block r = a;
     for (auto& e : r.terms) e.second *= c;
     drop_zero_terms(r);
-    r.cst *= c; r.deg *= c; r.nl *= c;
+    r.cst *= c; r.deg *= c; r.nl *= c; r.nv *= c * c;
     return r;
 }
 Block complement(const Block& a, int top) {
@@ -97,7 +104,7 @@ std::vector<Block> Evaluator::level(const std::vector<Req>& reqs) {
             out[i] = Block::constant(r.lut[r.in.cst]);
             continue;
         }
-        if (r.in.nl > kMaxNoise) throw RadixError("level: noise budget exceeded before a bootstrap");
+        if (!within_noise_budget(r.in)) throw RadixError("level: noise budget exceeded before a bootstrap");
         LevelReq q;
         for (const auto& e : r.in.terms) q.terms.emplace_back(e.first->idx, e.second);
         q.cst = r.in.cst;
@@ -124,6 +131,7 @@ void Evaluator::materialize(Radix& r) {
         q.cst = b.cst;
         q.dst = be_->alloc_slot();
         Block nb = Block::from_slot(std::make_shared<SlotRef>(be_, q.dst), b.deg, b.nl);
+        nb.nv = b.nv;
         lin.push_back(std::move(q));
         // keep the sources alive until run_linear has been enqueued
         b.terms.swap(nb.terms);
@@ -367,11 +375,12 @@ Radix Evaluator::sum_columns(std::vector<std::vector<Block>>& cols) {
     // products.)
     auto needs_round = [&]() {
         for (int c = 0; c < n; ++c) {
-            int deg = 0, nl = 0;
-            for (const auto& b : cols[c]) { deg += b.deg; nl += b.nl; }
+            int deg = 0;
+            Block acc = Block::constant(0);
+            for (const auto& b : cols[c]) { deg += b.deg; acc.nl += b.nl; acc.nv += b.nv; }
             // the most significant column wraps: no state is derived from it, only its message (any sum below 15 + carry-in)
             const int limit = c == n - 1 ? (c == 0 ? 15 : 14) : (c == 0 ? 7 : 6);
-            if (deg > limit || nl > kMaxNoise) return true;
+            if (deg > limit || !within_noise_budget(acc)) return true;
         }
         return false;
     };
@@ -398,7 +407,7 @@ Radix Evaluator::sum_columns(std::vector<std::vector<Block>>& cols) {
             while (i < col.size()) {
                 Block s = col[i];
                 size_t j = i + 1;
-                while (j < col.size() && s.deg + col[j].deg < kSpace && s.nl + col[j].nl <= kMaxNoise) { s = s + col[j]; ++j; }
+                while (j < col.size() && s.deg + col[j].deg < kSpace && within_noise_budget(s + col[j])) { s = s + col[j]; ++j; }
                 if (j == i + 1) { nxt[c].push_back(col[i]); }
                 else {
                     reqs.push_back({s, lut_msg()}); dest.push_back(c);

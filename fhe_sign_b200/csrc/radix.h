@@ -35,6 +35,7 @@ constexpr int kMsgBits = 2;
 constexpr int kMsgMod = 4;          // message modulus
 constexpr int kSpace = 16;          // message * carry modulus
 constexpr int kMaxNoise = 5;        // max_noise_level of the parameter set
+constexpr int kMaxVariance = 25;    // the same budget in variance units (nu^2): opt-in bookkeeping, see noise_in_variance_units()
 constexpr size_t kBlocksPerGpuLevel = 148;   // widest PBS level that still runs at one ciphertext per SM (B200: 148 SMs)
 
 struct RadixError : std::runtime_error {
@@ -113,11 +114,12 @@ struct Block {
     int32_t cst = 0;
     int32_t deg = 0;
     int32_t nl = 0;
+    int32_t nv = 0;                     // noise variance in units of one fresh PBS output (sum of squared coefficients)
 
     bool trivial() const { return terms.empty(); }
     static Block constant(int v) { Block b; b.cst = v; b.deg = v; return b; }
     static Block from_slot(const SlotP& s, int deg, int nl = 1) {
-        Block b; b.terms.emplace_back(s, 1); b.deg = deg; b.nl = nl; return b;
+        Block b; b.terms.emplace_back(s, 1); b.deg = deg; b.nl = nl; b.nv = nl; return b;
     }
 };
 
@@ -125,6 +127,10 @@ Block operator+(const Block& a, const Block& b);
 Block operator*(const Block& a, int c);            // c >= 0
 Block complement(const Block& a, int top);         // top - a   (requires a <= top)
 Block add_const(const Block& a, int c);
+// FSC_RADIX_NOISE=variance: budget checks and column-sum chunking use sum c^2 <= 25 instead of sum |c| <= 5 (experimental:
+// the parameter set is designed for nu^2 = 25 sigma_pbs^2, but the relaxed packing has not been noise-measured on the GPU yet)
+bool noise_in_variance_units();
+inline bool within_noise_budget(const Block& b) { return noise_in_variance_units() ? b.nv <= kMaxVariance : b.nl <= kMaxNoise; }
 
 using Radix = std::vector<Block>;                   // little endian; blocks clean (deg <= 3) between operators
 
