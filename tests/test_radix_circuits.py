@@ -270,3 +270,31 @@ def test_rem_by_pseudo_mersenne_moduli_folds(M):
             if nb == 257:
                 assert p1 - p0 < 20000
     assert M.counters()["violations"] == 0
+
+
+def test_variance_unit_noise_bookkeeping_is_a_relaxation():
+    """FSC_RADIX_NOISE=variance (experimental, off by default): same decrypted results, fewer bootstraps in a wide product
+    (column-sum chunks may hold more low-degree terms).  The switch is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, random; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from mock_radix import MockRadix\n"
+        "m = MockRadix(); rnd = random.Random(5)\n"
+        "x, y, z = rnd.getrandbits(128), rnd.getrandbits(128), rnd.getrandbits(128)\n"
+        "p0, _ = m.api.stats()\n"
+        "s = m.api.mul_add_wide(m.enc(x, 64), m.enc(y, 64), m.enc(z, 64), 130)\n"
+        "p1, _ = m.api.stats()\n"
+        "assert m.dec(s) == x * y + z and m.counters()['violations'] == 0\n"
+        "a = m.enc(x & 0xFFFFFFFF, 16)\n"
+        "assert m.dec(a // 5) == (x & 0xFFFFFFFF) // 5 and m.dec(a * a) == ((x & 0xFFFFFFFF) ** 2) & 0xFFFFFFFF\n"
+        "print(p1 - p0)\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    counts = {}
+    for mode in ("linear", "variance"):
+        env = dict(os.environ, FSC_RADIX_NOISE=mode)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        counts[mode] = int(out.stdout.strip().splitlines()[-1])
+    assert counts["variance"] < counts["linear"]
