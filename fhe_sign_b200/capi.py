@@ -97,7 +97,7 @@ EXPORTS = ["fsc_ctx_create", "fsc_ctx_destroy", "fsc_last_error", "fsc_get_param
            "fsc_ks_pbs_batch", "fsc_apply_lut_host", "fsc_timer_start", "fsc_timer_stop", "fsc_launch_count",
            "fsc_debug_negacyclic_mul", "fsc_measure_fp64_peak", "fsc_pbs_kernel_name"]
 from .radix import RADIX_EXPORTS  # noqa: E402
-EXPORTS = EXPORTS + RADIX_EXPORTS + ["fsc_client_keygen", "fsc_client_free", "fsc_client_last_error", "fsc_client_server_keys",
+EXPORTS = EXPORTS + RADIX_EXPORTS + ["fsc_client_keygen", "fsc_client_keygen_seeded", "fsc_client_set_encryption_seed", "fsc_client_free", "fsc_client_last_error", "fsc_client_server_keys",
                                      "fsc_client_secret_keys", "fsc_client_encrypt_blocks", "fsc_client_decrypt_blocks",
                                      "fsc_client_save", "fsc_client_load", "fsc_server_keys_save", "fsc_server_keys_load",
                                      "fsc_blocks_save", "fsc_blocks_load", "fsc_buffer_free"]

@@ -23,7 +23,7 @@ class NoiseParams(C.Structure):
                 ("reserved", C.c_uint32), ("lwe_noise_std", C.c_double), ("glwe_noise_std", C.c_double)]
 
 
-CLIENT_EXPORTS = ["fsc_client_keygen", "fsc_client_free", "fsc_client_last_error", "fsc_client_server_keys",
+CLIENT_EXPORTS = ["fsc_client_keygen", "fsc_client_keygen_seeded", "fsc_client_set_encryption_seed", "fsc_client_free", "fsc_client_last_error", "fsc_client_server_keys",
                   "fsc_client_secret_keys", "fsc_client_encrypt_blocks", "fsc_client_decrypt_blocks",
                   "fsc_client_save", "fsc_client_load", "fsc_server_keys_save", "fsc_server_keys_load",
                   "fsc_blocks_save", "fsc_blocks_load", "fsc_buffer_free"]
@@ -31,7 +31,9 @@ CLIENT_EXPORTS = ["fsc_client_keygen", "fsc_client_free", "fsc_client_last_error
 
 def _declare(L):
     vp, sz = C.c_void_p, C.c_size_t
-    L.fsc_client_keygen.argtypes = [C.POINTER(Params), C.POINTER(NoiseParams), C.c_uint64, C.POINTER(vp)]
+    L.fsc_client_keygen.argtypes = [C.POINTER(Params), C.POINTER(NoiseParams), C.POINTER(vp)]
+    L.fsc_client_keygen_seeded.argtypes = [C.POINTER(Params), C.POINTER(NoiseParams), C.c_uint64, C.POINTER(vp)]
+    L.fsc_client_set_encryption_seed.argtypes = [vp, C.c_uint64]
     L.fsc_client_free.argtypes = [vp]
     L.fsc_client_last_error.argtypes = [vp]; L.fsc_client_last_error.restype = C.c_char_p
     L.fsc_client_server_keys.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(sz)]
@@ -48,9 +50,13 @@ def _declare(L):
 
 
 class ClientKey:
-    """Secret keys + the server key material derived from them (seeded)."""
+    """Secret keys + the server key material derived from them.
 
-    def __init__(self, preset="2_2_gaussian", seed=1, _handle=None, _params=None):
+    seed=None (default): 256-bit master key from the OS CSPRNG, like the reference's tfhe::generate_keys.
+    seed=<int>: TEST-ONLY deterministic keys (at most 64 bits of entropy).  Encryption masks and noise always come from a
+    fresh OS-entropy stream per instance unless `encryption_seed` pins them too (reproducible ciphertexts in tests)."""
+
+    def __init__(self, preset="2_2_gaussian", seed=None, encryption_seed=None, _handle=None, _params=None):
         self.L = load_library()
         _declare(self.L)
         if _handle is not None:      # ClientKey.load
@@ -59,10 +65,15 @@ class ClientKey:
         self.params = Params.preset(preset)
         self.noise = NoiseParams(**NOISE[preset])
         h = C.c_void_p()
-        rc = self.L.fsc_client_keygen(C.byref(self.params), C.byref(self.noise), seed, C.byref(h))
+        if seed is None:
+            rc = self.L.fsc_client_keygen(C.byref(self.params), C.byref(self.noise), C.byref(h))
+        else:
+            rc = self.L.fsc_client_keygen_seeded(C.byref(self.params), C.byref(self.noise), int(seed), C.byref(h))
         if rc != 0:
             raise FscError(rc, (self.L.fsc_client_last_error(None) or b"").decode())
         self.h = h
+        if encryption_seed is not None:
+            self._check(self.L.fsc_client_set_encryption_seed(self.h, int(encryption_seed)))
 
     def __del__(self):
         try:
@@ -78,7 +89,8 @@ class ClientKey:
 
     # ---- on-disk formats (csrc/keyfile.cpp) ---------------------------------------------------------------
     def save(self, path):
-        """seeded client key: parameters, noise, seed, secret bits (a few KB; server keys are re-derived on load)."""
+        """client key file: parameters, noise, 256-bit master key, secret bits (a few KB; server keys are re-derived on
+        load; no encryption state is stored).  Holds the secret key: protect it accordingly."""
         self._check(self.L.fsc_client_save(self.h, str(path).encode()))
 
     @classmethod
@@ -185,7 +197,8 @@ def load_blocks(path):
     return p, out
 
 
-def generate_keys(preset="2_2_gaussian", seed=1):
-    """tfhe::generate_keys look-alike: returns (client_key, (bsk_std, ksk))."""
-    ck = ClientKey(preset, seed)
+def generate_keys(preset="2_2_gaussian", seed=None, encryption_seed=None):
+    """tfhe::generate_keys look-alike: returns (client_key, (bsk_std, ksk)).  seed=None: OS entropy (the default, as in
+    the reference); an integer seed gives reproducible keys for tests and benches only."""
+    ck = ClientKey(preset, seed, encryption_seed)
     return ck, ck.server_keys()

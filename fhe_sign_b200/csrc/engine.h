@@ -57,8 +57,9 @@ struct Engine {
     cudaEvent_t chunk_event(size_t i);
     const uint32_t* stage_lut_idx(const uint32_t* lut_idx, size_t count, const Luts* luts);
     void keyswitch(const uint64_t* in_big, uint64_t* out_small, size_t count);
+    // dests: optional multi-destination output (the same block pool on every GPU of the node, fsc_peer_*); overrides out_big
     void pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut_idx_dev, uint64_t* out_big, size_t count,
-             const int32_t* out_idx_dev = nullptr);
+             const int32_t* out_idx_dev = nullptr, const OutDest* dests = nullptr);
     void ks_pbs(const uint64_t* in_big, const Luts* luts, const uint32_t* lut_idx_dev, uint64_t* out_big, size_t count);
 };
 

@@ -4,7 +4,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "fsc_internal.h"
@@ -15,6 +18,18 @@
 namespace fsc {
 
 static thread_local std::string g_create_error;
+
+void ensure_dynamic_smem(const void* kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> done;      // (kernel, device) -> bytes opted in
+    int dev = 0;
+    FSC_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = done[{kernel, dev}];
+    if (have >= bytes) return;
+    FSC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+}
 
 // ---- LUT polynomial construction (integer host code; what tfhe's generate_lookup_table does) ----
 void build_lut_poly(const fsc_params& p, const uint64_t* table, uint64_t* poly) {
@@ -103,6 +118,23 @@ Engine::~Engine() {
 
 void Engine::use() { FSC_CUDA_CHECK(cudaSetDevice(dev)); }
 
+namespace {
+// device allocation released on scope exit unless handed over (key upload builds everything in locals first)
+struct DevBuf {
+    void* p = nullptr;
+    DevBuf() {}
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    void alloc(size_t bytes) { FSC_CUDA_CHECK(cudaMalloc(&p, bytes)); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+    template <class T> T* release() { T* r = static_cast<T*>(p); p = nullptr; return r; }
+};
+}  // namespace
+
+// The new key buffers are built in locals and swapped into the engine only after the final stream sync succeeded:
+// a failure anywhere (allocation, copy, conversion launch) leaves the engine with NO keys (FSC_ERR_NO_KEYS on the
+// next batch call) instead of half-converted ones, and leaks nothing.
 void Engine::upload_keys(const uint64_t* bsk_std, size_t bsk_words, const uint64_t* ksk_h, size_t ksk_words) {
     use();
     const size_t n = p.lwe_dim, N = p.poly_size;
@@ -110,38 +142,40 @@ void Engine::upload_keys(const uint64_t* bsk_std, size_t bsk_words, const uint64
     FSC_REQUIRE(bsk_std && ksk_h, "null key pointer");
     FSC_REQUIRE(bsk_words == want_bsk, "bootstrapping key size does not match the parameter set");
     FSC_REQUIRE(ksk_words == want_ksk, "keyswitching key size does not match the parameter set");
+    FSC_CUDA_CHECK(cudaStreamSynchronize(stream));      // nothing in flight may still read the old keys
     if (bsk_f) { cudaFree(bsk_f); bsk_f = nullptr; }
     if (bsk_s) { cudaFree(bsk_s); bsk_s = nullptr; }
     if (ksk) { cudaFree(ksk); ksk = nullptr; }
     if (ksk_limbs) { cudaFree(ksk_limbs); ksk_limbs = nullptr; }
-    uint64_t* tmp = nullptr;
-    FSC_CUDA_CHECK(cudaMalloc(&tmp, want_bsk * 8));
-    cudaError_t e = cudaMalloc(&bsk_f, n * 32 * 4 * 32 * 16);
-    if (e != cudaSuccess) { cudaFree(tmp); FSC_CUDA_CHECK(e); }
-    e = cudaMalloc(&ksk, want_ksk * 8);
-    if (e != cudaSuccess) { cudaFree(tmp); FSC_CUDA_CHECK(e); }
-    FSC_CUDA_CHECK(cudaMemcpyAsync(tmp, bsk_std, want_bsk * 8, cudaMemcpyHostToDevice, stream));
-    FSC_CUDA_CHECK(cudaMemcpyAsync(ksk, ksk_h, want_ksk * 8, cudaMemcpyHostToDevice, stream));
-    pbs_variant = pbs_variant_for((int)p.acc_bits);
-    if (pbs_variant == 2 || pbs_variant == 4) launch_bsk_convert_stream(tmp, bsk_f, (int)n, stream);      // the stream kernel's key order
-    else launch_bsk_convert(tmp, bsk_f, (int)n, stream);
+    const size_t fourier_bytes = n * 32 * 4 * 32 * 16;
+    const int variant = pbs_variant_for((int)p.acc_bits);
+    DevBuf tmp, nf, ns, nk, nl;
+    tmp.alloc(want_bsk * 8);
+    nf.alloc(fourier_bytes);
+    nk.alloc(want_ksk * 8);
+    FSC_CUDA_CHECK(cudaMemcpyAsync(tmp.p, bsk_std, want_bsk * 8, cudaMemcpyHostToDevice, stream));
+    FSC_CUDA_CHECK(cudaMemcpyAsync(nk.p, ksk_h, want_ksk * 8, cudaMemcpyHostToDevice, stream));
+    if (variant == 2 || variant == 4) launch_bsk_convert_stream(tmp.as<uint64_t>(), nf.p, (int)n, stream);      // the stream kernel's key order
+    else launch_bsk_convert(tmp.as<uint64_t>(), nf.p, (int)n, stream);
     ++launches;
-    if (pbs_variant == 3) {      // both kernels: second copy of the Fourier key in the stream kernel's order
-        e = cudaMalloc(&bsk_s, n * 32 * 4 * 32 * 16);
-        if (e != cudaSuccess) { cudaFree(tmp); FSC_CUDA_CHECK(e); }
-        launch_bsk_convert_stream(tmp, bsk_s, (int)n, stream);
-        ++launches;
-    }
     FSC_CUDA_CHECK(cudaGetLastError());
-    {
-        const size_t K = (size_t)N * p.ks_level;
-        e = cudaMalloc(&ksk_limbs, ks_mma_limb_rows((int)n) * K);
-        if (e != cudaSuccess) { cudaFree(tmp); FSC_CUDA_CHECK(e); }
-        launch_ksk_limb_transpose(ksk, ksk_limbs, (int)K, (int)n, stream); ++launches;
+    if (variant == 3) {      // both kernels: second copy of the Fourier key in the stream kernel's order
+        ns.alloc(fourier_bytes);
+        launch_bsk_convert_stream(tmp.as<uint64_t>(), ns.p, (int)n, stream);
+        ++launches;
         FSC_CUDA_CHECK(cudaGetLastError());
     }
+    const size_t K = (size_t)N * p.ks_level;
+    nl.alloc(ks_mma_limb_rows((int)n) * K);
+    launch_ksk_limb_transpose(nk.as<uint64_t>(), nl.as<uint8_t>(), (int)K, (int)n, stream);
+    ++launches;
+    FSC_CUDA_CHECK(cudaGetLastError());
     FSC_CUDA_CHECK(cudaStreamSynchronize(stream));
-    cudaFree(tmp);
+    pbs_variant = variant;
+    bsk_f = nf.release<void>();
+    bsk_s = ns.release<void>();
+    ksk = nk.release<uint64_t>();
+    ksk_limbs = nl.release<uint8_t>();
 }
 
 void Engine::ensure_scratch(size_t count) {
@@ -213,23 +247,23 @@ void Engine::keyswitch(const uint64_t* in_big, uint64_t* out_small, size_t count
 }
 
 void Engine::pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut_idx_dev, uint64_t* out_big, size_t count,
-                 const int32_t* out_idx_dev) {
+                 const int32_t* out_idx_dev, const OutDest* dests) {
     use();
     if (!bsk_f) throw Error(FSC_ERR_NO_KEYS, "server keys not uploaded");
-    // variant 3: narrow levels (at most two ciphertexts per SM: the latency-bound case) on the stream kernel, wide
-    // batches on the ring kernel
-    // variant 3: levels of at most one ciphertext per SM on the split kernel (four warps per ciphertext),
+    const OutDest od = dests ? *dests : single_dest(out_big);
+    // variant 3: levels of at most one ciphertext per SM on the split kernel (four warps per ciphertext: the latency-bound
+    // case), up to two per SM on the stream kernel, wide batches on the ring kernel
     if (pbs_variant == 4 || (pbs_variant == 3 && use_split && (int)count <= sm_count))
         launch_pbs_split((int)p.acc_bits, pbs_variant == 4 ? bsk_f : bsk_s, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d,
-                         lut_idx_dev, out_big, out_idx_dev, (int)count, stream);
+                         lut_idx_dev, od, out_idx_dev, (int)count, stream);
     else if (pbs_variant == 3 && (int)count <= 2 * sm_count)
-        launch_pbs_stream((int)p.acc_bits, bsk_s, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, out_big,
+        launch_pbs_stream((int)p.acc_bits, bsk_s, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, od,
                           out_idx_dev, (int)count, sm_count, stream);
     else if (pbs_variant == 2)
-        launch_pbs_stream((int)p.acc_bits, bsk_f, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, out_big,
+        launch_pbs_stream((int)p.acc_bits, bsk_f, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, od,
                           out_idx_dev, (int)count, sm_count, stream);
     else
-        launch_pbs(pbs_variant, (int)p.acc_bits, bsk_f, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, out_big,
+        launch_pbs(pbs_variant, (int)p.acc_bits, bsk_f, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, od,
                    out_idx_dev, (int)count, sm_count, stream);
     ++launches;
     FSC_CUDA_CHECK(cudaGetLastError());

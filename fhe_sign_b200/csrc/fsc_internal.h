@@ -27,22 +27,50 @@ struct Error : std::runtime_error {
         if (!(cond)) throw ::fsc::Error(FSC_ERR_BAD_ARG, (msg));        \
     } while (0)
 
+// Where a blind rotation writes its output ciphertext: base[0] is the local destination array; with level sharding over
+// peer-mapped block pools (radix_cuda.cu, fsc_peer_*) base[1 .. n) are the SAME pool on the other GPUs of the node, and the
+// sample-extraction epilogue stores every word to all of them over NVLink - the exchange is fused into the kernel.
+constexpr int kMaxPeers = 8;
+struct OutDest {
+    uint64_t* base[kMaxPeers];
+    int n;
+};
+#ifdef __CUDACC__
+// one extracted word to every destination pool (local store + NVLink peer stores; d.n is uniform across the grid)
+__device__ __forceinline__ void store_out_word(const OutDest& d, size_t off, uint64_t w) {
+    d.base[0][off] = w;
+#pragma unroll 1
+    for (int i = 1; i < d.n; ++i) d.base[i][off] = w;
+}
+#endif
+inline OutDest single_dest(uint64_t* out_big) {
+    OutDest d;
+    for (int i = 0; i < kMaxPeers; ++i) d.base[i] = nullptr;
+    d.base[0] = out_big; d.n = 1;
+    return d;
+}
+
+// fsc_api.cu: opts `kernel` into `bytes` of dynamic shared memory on the CURRENT device, once per (kernel, device).
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: a process-wide flag would leave a second
+// context on another GPU with the 48 KB default.  Thread-safe.
+void ensure_dynamic_smem(const void* kernel, size_t bytes);
+
 // pbs_kernel.cu
 void pbs_init_constants();
 void launch_bsk_convert(const uint64_t* bsk_std, void* bsk_fourier, int n, cudaStream_t st);
 void launch_pbs(int variant, int acc_bits, const void* bsk_fourier, const uint64_t* in_small, int n, int base_log,
-                const uint64_t* luts, const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count,
+                const uint64_t* luts, const uint32_t* lut_idx, const OutDest& out_big, const int32_t* out_idx, int count,
                 int sm_count, cudaStream_t st);
 void launch_negacyclic_mul(const uint64_t* a, const int64_t* b, uint64_t* c, int count, cudaStream_t st);
 
 // pbs_stream_kernel.cu (single-routine formulation; its own Fourier key layout)
 void launch_bsk_convert_stream(const uint64_t* bsk_std, void* bsk_fourier, int n, cudaStream_t st);
 void launch_pbs_stream(int acc_bits, const void* bsk_fourier, const uint64_t* in_small, int n, int base_log,
-                       const uint64_t* luts, const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count,
+                       const uint64_t* luts, const uint32_t* lut_idx, const OutDest& out_big, const int32_t* out_idx, int count,
                        int sm_count, cudaStream_t st);
 // pbs_split_kernel.cu (latency form for narrow levels: four warps per ciphertext; the stream kernel's key layout)
 void launch_pbs_split(int acc_bits, const void* bsk_fourier, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
-                      const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st);
+                      const uint32_t* lut_idx, const OutDest& out_big, const int32_t* out_idx, int count, cudaStream_t st);
 void launch_negacyclic_mul_stream(const uint64_t* a, const int64_t* b, uint64_t* c, int count, cudaStream_t st);
 // 0: pair, 1: ring, 2: stream, 3: ring (wide) + stream (narrow) (FSC_PBS_VARIANT, else by accumulator width);
 // fixed per context at key upload
@@ -72,5 +100,8 @@ void launch_lincomb(const uint64_t* pool, const int32_t* row_ptr, const int32_t*
                     cudaStream_t st);
 
 void launch_scatter(const uint64_t* buffer, const int32_t* dst_idx, uint64_t* pool, int count, int words, cudaStream_t st);
+// flag barrier over peer-mapped memory: remote_flags[q] = flag array in rank q's pool allocation (q = rank: local)
+void launch_peer_barrier(uint64_t* const* remote_flags, uint64_t* err, int rank, int world, uint64_t seq, cudaStream_t st);
+void launch_gather(const uint64_t* pool, const int32_t* src_idx, uint64_t* buffer, int count, int words, cudaStream_t st);
 
 }  // namespace fsc

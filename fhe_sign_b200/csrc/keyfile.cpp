@@ -10,14 +10,19 @@
 //   16  u32[10]  fsc_params   (lwe_dim, glwe_dim, poly_size, pbs_base_log, pbs_level, ks_base_log, ks_level,
 //                              message_modulus, carry_modulus, acc_bits)
 //   56  fsc_noise_params (32 bytes; zero for kinds 2 and 3)
-//   88  u64      seed (kind 1; 0 otherwise)
-//   96  u64      aux  (kind 1: encryption counter; kind 3: number of blocks)
+//   88  u64      reserved (0)
+//   96  u64      aux  (kind 2: bsk word count; kind 3: number of blocks; kind 1: 0)
 //   104 u64      payload words (u64 count)
-//   112 payload  kind 1: lwe_sk | glwe_sk as bit-per-word u64 (the keys are re-derived from the seed on load and must
-//                        equal these; bsk / ksk are NOT stored: 123 MB regenerate in well under a second)
+//   112 payload  kind 1: 256-bit master key (4 words) | lwe_sk | glwe_sk as bit-per-word u64 (the keys are re-derived
+//                        from the master key on load and must equal these; bsk / ksk are NOT stored: 123 MB regenerate
+//                        in well under a second).  NO encryption state is stored: encryption masks and noise come from
+//                        a fresh OS-entropy stream per client instance, so save -> encrypt -> load, or one file loaded
+//                        by two processes, can never replay a mask.  The file holds the secret key: protect it as such.
 //                kind 2: bsk [n][k+1][l][k+1][N] | ksk [kN][l_ks][n+1]     (the layout fsc_keys_upload takes)
 //                kind 3: n_blocks x (k N + 1) words, mask first, body last
-//   ...  u64     FNV-1a 64 checksum of every byte before it
+//   ...  u64     FNV-1a 64 checksum of every byte before it (detects truncation / corruption; it is NOT a MAC -
+//                authenticate key files by other means if they cross a trust boundary).  Header fields that feed shift
+//                amounts or allocation sizes are range-checked before use.
 //
 // No C++ exception crosses the boundary; errors come back as fsc_status with fsc_client_last_error(NULL).
 #include <stdint.h>
@@ -33,7 +38,7 @@
 namespace {
 
 constexpr char kMagic[8] = {'F', 'S', 'C', 'F', 'I', 'L', 'E', '1'};
-constexpr uint32_t kVersion = 1;
+constexpr uint32_t kVersion = 2;      // 2: master key in the payload, no encryption counter
 
 struct Header {
     char magic[8];
@@ -116,12 +121,14 @@ fsc_status fsc_client_save(const fsc_client* c, const char* path) {
     if (!c || !path) return fail(FSC_ERR_BAD_ARG, "null argument");
     Header h = make_header(1, fsc_client_params(c));
     h.noise = fsc_client_noise(c);
-    h.seed = fsc_client_seed(c);
-    h.aux = fsc_client_enc_counter(c);
     const uint64_t *lwe = nullptr, *glwe = nullptr;
     fsc_client_secret_keys(c, &lwe, &glwe);
     const fsc_params p = fsc_client_params(c);
-    return write_file(path, h, {{lwe, p.lwe_dim}, {glwe, (size_t)p.glwe_dim * p.poly_size}});
+    uint64_t master[4];
+    memcpy(master, fsc_client_master_key(c), 32);
+    const fsc_status st = write_file(path, h, {{master, 4}, {lwe, p.lwe_dim}, {glwe, (size_t)p.glwe_dim * p.poly_size}});
+    memset(master, 0, sizeof(master));
+    return st;
 }
 
 fsc_status fsc_client_load(const char* path, fsc_client** out) {
@@ -133,19 +140,20 @@ fsc_status fsc_client_load(const char* path, fsc_client** out) {
     if (st != FSC_OK) return st;
     fsc_params p;
     memcpy(&p, h.params, sizeof(p));
-    if (payload.size() != (uint64_t)p.lwe_dim + (uint64_t)p.glwe_dim * p.poly_size) return fail(FSC_ERR_BAD_ARG, "secret key size does not match the parameters");
+    std::string why;
+    if (!fsc_params_plausible(p, h.noise, &why)) return fail(FSC_ERR_PARAMS, "key file header: " + why);      // before any shift or allocation derived from it
+    if (payload.size() != 4 + (uint64_t)p.lwe_dim + (uint64_t)p.glwe_dim * p.poly_size) return fail(FSC_ERR_BAD_ARG, "secret key size does not match the parameters");
     fsc_client* c = nullptr;
-    st = fsc_client_keygen(&p, &h.noise, h.seed, &c);
+    st = fsc_client_keygen_from_master(&p, &h.noise, reinterpret_cast<const uint8_t*>(payload.data()), &c);
     if (st != FSC_OK) return st;
     const uint64_t *lwe = nullptr, *glwe = nullptr;
     fsc_client_secret_keys(c, &lwe, &glwe);
-    if (memcmp(lwe, payload.data(), (size_t)p.lwe_dim * 8) != 0 ||
-        memcmp(glwe, payload.data() + p.lwe_dim, (size_t)p.glwe_dim * p.poly_size * 8) != 0) {
+    if (memcmp(lwe, payload.data() + 4, (size_t)p.lwe_dim * 8) != 0 ||
+        memcmp(glwe, payload.data() + 4 + p.lwe_dim, (size_t)p.glwe_dim * p.poly_size * 8) != 0) {
         fsc_client_free(c);
-        return fail(FSC_ERR_INTERNAL, "the seed does not regenerate the stored secret key (different library version?)");
+        return fail(FSC_ERR_INTERNAL, "the master key does not regenerate the stored secret key (different library version?)");
     }
-    fsc_client_set_enc_counter(c, h.aux);      // never reuse encryption randomness across a save / load
-    *out = c;
+    *out = c;      // encryption randomness of the new instance is fresh OS entropy (nothing of it is persisted)
     return FSC_OK;
 }
 
@@ -168,6 +176,10 @@ fsc_status fsc_server_keys_load(const char* path, fsc_params* params, uint64_t**
     if (st != FSC_OK) return st;
     fsc_params p;
     memcpy(&p, h.params, sizeof(p));
+    fsc_noise_params none;
+    memset(&none, 0, sizeof(none));
+    std::string why;
+    if (!fsc_params_plausible(p, none, &why)) return fail(FSC_ERR_PARAMS, "key file header: " + why);
     if (h.aux > payload.size() || !words_match(p, h.aux, payload.size() - h.aux)) return fail(FSC_ERR_BAD_ARG, "key sizes do not match the parameters");
     uint64_t* buf = new (std::nothrow) uint64_t[payload.size() ? payload.size() : 1];
     if (!buf) return fail(FSC_ERR_OOM, "host allocation failed");
@@ -194,8 +206,12 @@ fsc_status fsc_blocks_load(const char* path, fsc_params* params, uint64_t** bloc
     if (st != FSC_OK) return st;
     fsc_params p;
     memcpy(&p, h.params, sizeof(p));
+    fsc_noise_params none;
+    memset(&none, 0, sizeof(none));
+    std::string why;
+    if (!fsc_params_plausible(p, none, &why)) return fail(FSC_ERR_PARAMS, "block file header: " + why);
     const uint64_t words = (uint64_t)p.glwe_dim * p.poly_size + 1;
-    if (payload.size() != h.aux * words) return fail(FSC_ERR_BAD_ARG, "block count does not match the payload");
+    if (h.aux > ((uint64_t)1 << 34) / words || payload.size() != h.aux * words) return fail(FSC_ERR_BAD_ARG, "block count does not match the payload");
     uint64_t* buf = new (std::nothrow) uint64_t[payload.size() ? payload.size() : 1];
     if (!buf) return fail(FSC_ERR_OOM, "host allocation failed");
     memcpy(buf, payload.data(), payload.size() * 8);

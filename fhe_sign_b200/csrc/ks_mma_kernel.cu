@@ -197,11 +197,7 @@ void launch_keyswitch_mma(const uint8_t* limbs, int8_t* digits, const uint64_t* 
     const int rows_pad = (int)ks_mma_digit_rows(count);
     ks_decompose_kernel<<<592, 256, 0, st>>>(in_big, digits, count, rows_pad, big_dim, base_log, level);
     const size_t smem = (size_t)MM_STAGES * (MM_BM + MM_BN) * MM_BK;
-    static bool configured = false;
-    if (!configured) {
-        FSC_CUDA_CHECK(cudaFuncSetAttribute(ks_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    ensure_dynamic_smem(reinterpret_cast<const void*>(&ks_mma_kernel), smem);      // per device (the opt-in is a per-device attribute)
     dim3 grid((unsigned)(ks_mma_limb_rows(n) / MM_BN), (unsigned)(rows_pad / MM_BM));
     ks_mma_kernel<<<grid, MM_THREADS, smem, st>>>(digits, limbs, in_big, out_small, count, K, big_dim, n);
 }

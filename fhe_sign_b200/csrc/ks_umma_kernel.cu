@@ -226,11 +226,7 @@ void launch_keyswitch_umma(const uint8_t* limbs, size_t limb_rows, const int8_t*
     const CUtensorMap md = um_make_map(digits, (uint64_t)rows_pad, (uint64_t)K, UM_BM);
     const CUtensorMap mb = um_make_map(limbs, (uint64_t)limb_rows, (uint64_t)K, UM_BN);
     const size_t smem = (size_t)UM_STAGES * (UM_A_BYTES + UM_B_BYTES) + 1024 + 256;
-    static bool configured = false;
-    if (!configured) {
-        FSC_CUDA_CHECK(cudaFuncSetAttribute(ks_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    ensure_dynamic_smem(reinterpret_cast<const void*>(&ks_umma_kernel), smem);      // per device (the opt-in is a per-device attribute)
     dim3 grid((unsigned)(limb_rows / UM_BN), (unsigned)(rows_pad / UM_BM));
     ks_umma_kernel<<<grid, UM_THREADS, smem, st>>>(md, mb, in_big, out_small, count, K, big_dim, n);
 }

@@ -37,6 +37,53 @@ void launch_scatter(const uint64_t* buffer, const int32_t* dst_idx, uint64_t* po
     scatter_kernel<<<count, 256, 0, st>>>(buffer, dst_idx, pool, words);
 }
 
+// buffer[b] = pool[src[b]]  (collecting the blocks of a radix value for one contiguous download)
+__global__ void __launch_bounds__(256) gather_kernel(const uint64_t* __restrict__ pool, const int32_t* __restrict__ src_idx,
+                                                      uint64_t* __restrict__ buffer, int words) {
+    const int b = blockIdx.x;
+    const uint64_t* src = pool + (size_t)src_idx[b] * words;
+    uint64_t* o = buffer + (size_t)b * words;
+    for (int w = threadIdx.x; w < words; w += blockDim.x) o[w] = src[w];
+}
+void launch_gather(const uint64_t* pool, const int32_t* src_idx, uint64_t* buffer, int count, int words, cudaStream_t st) {
+    if (count <= 0) return;
+    gather_kernel<<<count, 256, 0, st>>>(pool, src_idx, buffer, words);
+}
+
+// ---------------------------------------------------------------------------------------
+// Flag barrier between the ranks of a node over peer-mapped memory (level sharding, radix_cuda.cu).
+// Lane q tells peer q "rank `rank` has reached barrier `seq`" - every kernel this rank launched before, including the
+// blind rotation whose epilogue stored into the peers' pools, has completed (stream order), and the release at system
+// scope publishes those stores - then waits until peer q's arrival shows up in the local flags.  The spin is bounded:
+// on timeout the barrier records `seq` in *err and returns (reported as FSC_ERR_COMM at the next download).
+// ---------------------------------------------------------------------------------------
+struct PeerFlags {
+    uint64_t* remote[kMaxPeers];      // remote[q] = flag array inside rank q's pool allocation (remote[rank] is local)
+    uint64_t* err;
+    int rank, world;
+};
+__global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ PeerFlags pf, uint64_t seq, long long timeout_cycles) {
+    const int q = threadIdx.x;
+    if (q >= pf.world) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pf.remote[q] + pf.rank), "l"(seq) : "memory");
+    const uint64_t* mine = pf.remote[pf.rank] + q;
+    const long long t0 = clock64();
+    for (;;) {
+        uint64_t v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+        if (v >= seq) break;
+        if (clock64() - t0 > timeout_cycles) { *pf.err = seq; break; }
+        __nanosleep(200);
+    }
+}
+void launch_peer_barrier(uint64_t* const* remote_flags, uint64_t* err, int rank, int world, uint64_t seq, cudaStream_t st) {
+    PeerFlags pf;
+    for (int i = 0; i < kMaxPeers; ++i) pf.remote[i] = i < world ? remote_flags[i] : nullptr;
+    pf.err = err; pf.rank = rank; pf.world = world;
+    peer_barrier_kernel<<<1, 32, 0, st>>>(pf, seq, 8000000000ll);      // about 4 s at the B200's 1.9 GHz
+}
+
 void launch_lincomb(const uint64_t* pool, const int32_t* row_ptr, const int32_t* slot, const int32_t* coef, const int32_t* cst,
                     uint64_t delta, uint64_t* out, const int32_t* dst_idx, int count, int words, cudaStream_t st) {
     if (count <= 0) return;

@@ -148,7 +148,7 @@ constexpr int kGDepth = 4;      // register prefetch depth (frequency slots) of 
 template <typename AccT>
 __global__ void __launch_bounds__(64, 4) pbs_pair_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                        int n, int base_log, const uint64_t* __restrict__ luts,
-                                                       const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
+                                                       const uint32_t* __restrict__ lut_idx, const __grid_constant__ OutDest out_big,
                                                        const int32_t* __restrict__ out_idx, int count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -219,8 +219,8 @@ __global__ void __launch_bounds__(64, 4) pbs_pair_kernel(const cplx* __restrict_
     }
     __syncthreads();
 
-    uint64_t* out = out_big + (size_t)(out_idx ? out_idx[c] : c) * (kN + 1);
-    for (int j = threadIdx.x; j <= kN; j += 64) out[j] = extract_word<AccT>(acc_all, acc_all + 1024, j);
+    const size_t out = (size_t)(out_idx ? out_idx[c] : c) * (kN + 1);
+    for (int j = threadIdx.x; j <= kN; j += 64) store_out_word(out_big, out + j, extract_word<AccT>(acc_all, acc_all + 1024, j));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(64, 4) pbs_pair_kernel(const cplx* __restrict_
 template <typename AccT, int CTS, int NCH, bool XH, bool HS, bool TX>
 __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                                      int n, int base_log, const uint64_t* __restrict__ luts,
-                                                                     const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
+                                                                     const uint32_t* __restrict__ lut_idx, const __grid_constant__ OutDest out_big,
                                                                      const int32_t* __restrict__ out_idx, int count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pair_t<AccT>* acc_all = reinterpret_cast<pair_t<AccT>*>(smem_raw);
@@ -592,9 +592,9 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
     pair_barrier(1 + ctl);
 
     if (live) {
-        uint64_t* out = out_big + (size_t)(out_idx ? out_idx[c] : c) * (kN + 1);
+        const size_t out = (size_t)(out_idx ? out_idx[c] : c) * (kN + 1);
         const pair_t<AccT>* mask = acc_all + (size_t)(ctl * 2) * 1024;
-        for (int j = (p * 32 + lane); j <= kN; j += 64) out[j] = extract_word<AccT>(mask, mask + 1024, j);
+        for (int j = (p * 32 + lane); j <= kN; j += 64) store_out_word(out_big, out + j, extract_word<AccT>(mask, mask + 1024, j));
     }
     if (TX) {
         tmem_fence_before();
@@ -645,27 +645,19 @@ void launch_bsk_convert(const uint64_t* bsk, void* out, int n, cudaStream_t st) 
 
 template <typename AccT>
 static void launch_pbs_pair_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
-                              const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
+                              const uint32_t* lut_idx, const OutDest& out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     const size_t smem = 2 * 1024 * sizeof(pair_t<AccT>) + 2 * 1024 * sizeof(cplx);
-    static bool configured = false;
-    if (!configured) {
-        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_pair_kernel<AccT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    ensure_dynamic_smem(reinterpret_cast<const void*>(&pbs_pair_kernel<AccT>), smem);      // per device (the opt-in is a per-device attribute)
     pbs_pair_kernel<AccT><<<count, 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts,
                                                     lut_idx, out_big, out_idx, count);
 }
 
 template <typename AccT, int CTS, int NCH, bool XH, bool HS, bool TX = false>
 static void launch_pbs_ring_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
-                              const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
+                              const uint32_t* lut_idx, const OutDest& out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     const size_t smem = (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>) + (size_t)CTS * 2 * (XH ? 512 : 1024) * sizeof(cplx) +
                         (size_t)NCH * (HS ? kHalfCplx : kChunkCplx) * sizeof(cplx) + 16 * 32 * sizeof(cplx) + 2 * NCH * sizeof(uint64_t) + 16;
-    static bool configured = false;
-    if (!configured) {
-        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_ring_kernel<AccT, CTS, NCH, XH, HS, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    ensure_dynamic_smem(reinterpret_cast<const void*>(&pbs_ring_kernel<AccT, CTS, NCH, XH, HS, TX>), smem);      // per device (the opt-in is a per-device attribute)
     const int grid = (count + CTS - 1) / CTS;
     pbs_ring_kernel<AccT, CTS, NCH, XH, HS, TX><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log,
                                                                         luts, lut_idx, out_big, out_idx, count);
@@ -691,7 +683,7 @@ int pbs_variant_for(int acc_bits) {
 // ciphertext gets a less contended SM and the whole step's key fits in the ring - that is the latency-bound case
 // of the carry-propagation levels.
 void launch_pbs(int variant, int acc_bits, const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
-                const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, int sm_count, cudaStream_t st) {
+                const uint32_t* lut_idx, const OutDest& out_big, const int32_t* out_idx, int count, int sm_count, cudaStream_t st) {
     if (count <= 0) return;
     // ring kernel, half-step key ring (NH stages of 32 KB): wide levels pack 4 (u32 accumulator) or 3 (u64) ciphertexts
     // per CTA so that one key copy feeds them all; levels of at most one or two ciphertexts per SM use 1 or 2 per CTA

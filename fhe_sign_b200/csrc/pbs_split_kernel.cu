@@ -83,7 +83,7 @@ __device__ __forceinline__ void poly_barrier(int p) {      // the two warps of o
 template <typename AccT, int NH, int PX>
 __global__ void __launch_bounds__(128, 1) pbs_split_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                             int n, int base_log, const uint64_t* __restrict__ luts,
-                                                            const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
+                                                            const uint32_t* __restrict__ lut_idx, const __grid_constant__ OutDest out_big,
                                                             const int32_t* __restrict__ out_idx, int count,
                                                             const cplx* __restrict__ tabs_g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -245,28 +245,24 @@ __global__ void __launch_bounds__(128, 1) pbs_split_kernel(const cplx* __restric
 #undef FSC_POLL
     __syncthreads();
 
-    uint64_t* out = out_big + (size_t)(out_idx ? out_idx[c] : c) * (kN + 1);
-    for (int j = threadIdx.x; j <= kN; j += 128) out[j] = extract_word<AccT>(acc_all, acc_all + 1024, j);
+    const size_t out = (size_t)(out_idx ? out_idx[c] : c) * (kN + 1);
+    for (int j = threadIdx.x; j <= kN; j += 128) store_out_word(out_big, out + j, extract_word<AccT>(acc_all, acc_all + 1024, j));
 }
 
 template <typename AccT, int NH, int PX>
 static void launch_pbs_split_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
-                               const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
+                               const uint32_t* lut_idx, const OutDest& out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     const size_t smem = (size_t)2 * 1024 * sizeof(pair_t<AccT>) + (size_t)2 * (kSplitECplx + kSplitTCplx) * sizeof(cplx) +
                         (size_t)NH * kHalfCplx * sizeof(cplx) + (size_t)kTabCplx * sizeof(cplx) + 2 * NH * sizeof(uint64_t) +
                         (PX == 2 ? (size_t)2 * kSplitX2Cplx : PX == 1 ? (size_t)2 * kSplitXCplx : 0) * sizeof(cplx);
-    static bool configured = false;
-    if (!configured) {
-        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_split_kernel<AccT, NH, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    ensure_dynamic_smem(reinterpret_cast<const void*>(&pbs_split_kernel<AccT, NH, PX>), smem);      // per device (the opt-in is a per-device attribute)
     pbs_split_kernel<AccT, NH, PX><<<count, 128, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts, lut_idx,
                                                          out_big, out_idx, count, stream_tables<AccT>());
 }
 
 // bsk_f: the stream kernel's Fourier key (launch_bsk_convert_stream).  One CTA per ciphertext: meant for count <= SMs.
 void launch_pbs_split(int acc_bits, const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
-                      const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
+                      const uint32_t* lut_idx, const OutDest& out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     if (count <= 0) return;
 #define FSC_SPLIT(ACC, NH, PX) launch_pbs_split_t<ACC, NH, PX>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st)
     const char* cfg = getenv("FSC_SPLIT_CFG");      // comparison switch: "3r" = three-stage ring + redundant product, "2r", "22" = rolled step (measured 1-3 % slower); default: split product, unrolled

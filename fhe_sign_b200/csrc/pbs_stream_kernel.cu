@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(32) bsk_convert_stream_kernel(const uint64_t* 
 template <typename AccT, int CTS, int NH>
 __global__ void __launch_bounds__(CTS * 64, 1) pbs_stream_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                                   int n, int base_log, const uint64_t* __restrict__ luts,
-                                                                  const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
+                                                                  const uint32_t* __restrict__ lut_idx, const __grid_constant__ OutDest out_big,
                                                                   const int32_t* __restrict__ out_idx, int count,
                                                                   const cplx* __restrict__ tabs_g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -226,9 +226,9 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_stream_kernel(const cplx* __r
     pair_barrier(1 + ctl);
 
     if (live) {
-        uint64_t* out = out_big + (size_t)(out_idx ? out_idx[c] : c) * (kN + 1);
+        const size_t out = (size_t)(out_idx ? out_idx[c] : c) * (kN + 1);
         const pair_t<AccT>* mask = acc_all + (size_t)(ctl * 2) * 1024;
-        for (int j = (p * 32 + lane); j <= kN; j += 64) out[j] = extract_word<AccT>(mask, mask + 1024, j);
+        for (int j = (p * 32 + lane); j <= kN; j += 64) store_out_word(out_big, out + j, extract_word<AccT>(mask, mask + 1024, j));
     }
 }
 
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_stream_kernel(const cplx* __r
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                                  int n, int base_log, const uint64_t* __restrict__ luts,
-                                                                 const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out_big,
+                                                                 const uint32_t* __restrict__ lut_idx, const __grid_constant__ OutDest out_big,
                                                                  const int32_t* __restrict__ out_idx, int count,
                                                                  const cplx* __restrict__ tabs_g) {
     typedef uint32_t AccT;
@@ -486,9 +486,9 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
     pair_barrier(1 + ctl);
 
     if (live) {
-        uint64_t* out = out_big + (size_t)(out_idx ? out_idx[c] : c) * (kN + 1);
+        const size_t out = (size_t)(out_idx ? out_idx[c] : c) * (kN + 1);
         const pair_t<AccT>* mask = acc_all + (size_t)(ctl * 2) * 1024;
-        for (int j = (p * 32 + lane); j <= kN; j += 64) out[j] = extract_word<AccT>(mask, mask + 1024, j);
+        for (int j = (p * 32 + lane); j <= kN; j += 64) store_out_word(out_big, out + j, extract_word<AccT>(mask, mask + 1024, j));
     }
     tmem_fence_before();
     __syncthreads();
@@ -550,28 +550,20 @@ void launch_negacyclic_mul_stream(const uint64_t* a, const int64_t* b, uint64_t*
 
 template <typename AccT, int CTS, int NH>
 static void launch_pbs_stream_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
-                                const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
+                                const uint32_t* lut_idx, const OutDest& out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     const size_t smem = (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>) + (size_t)CTS * 2 * kXBufDoubles * sizeof(double) +
                         (size_t)NH * kHalfCplx * sizeof(cplx) + (size_t)kTabCplx * sizeof(cplx) + 2 * NH * sizeof(uint64_t);
-    static bool configured = false;
-    if (!configured) {
-        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_stream_kernel<AccT, CTS, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    ensure_dynamic_smem(reinterpret_cast<const void*>(&pbs_stream_kernel<AccT, CTS, NH>), smem);      // per device (the opt-in is a per-device attribute)
     const int grid = (count + CTS - 1) / CTS;
     pbs_stream_kernel<AccT, CTS, NH><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts,
                                                                           lut_idx, out_big, out_idx, count, stream_tables<AccT>());
 }
 
 static void launch_pbs_stream_tx(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
-                                 const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, cudaStream_t st) {
+                                 const uint32_t* lut_idx, const OutDest& out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     const size_t smem = (size_t)4 * 2 * 1024 * sizeof(pair_t<uint32_t>) + (size_t)4 * 2 * kXBufDoubles * sizeof(double) +
                         (size_t)2 * kHalfCplx * sizeof(cplx) + (size_t)kTabTwist * sizeof(cplx) + 2 * 2 * sizeof(uint64_t) + 16;
-    static bool configured = false;
-    if (!configured) {
-        FSC_CUDA_CHECK(cudaFuncSetAttribute(pbs_stream_tx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    ensure_dynamic_smem(reinterpret_cast<const void*>(&pbs_stream_tx_kernel), smem);      // per device (the opt-in is a per-device attribute)
     pbs_stream_tx_kernel<<<(count + 3) / 4, 256, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts, lut_idx,
                                                              out_big, out_idx, count, stream_tables<uint32_t>());
 }
@@ -580,7 +572,7 @@ static void launch_pbs_stream_tx(const void* bsk_f, const uint64_t* in_small, in
 // chunk feeds them all; levels of at most one or two ciphertexts per SM use 1 or 2 per CTA (the latency-bound case of
 // the carry-propagation levels: a less contended SM per ciphertext).
 void launch_pbs_stream(int acc_bits, const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
-                       const uint32_t* lut_idx, uint64_t* out_big, const int32_t* out_idx, int count, int sm_count, cudaStream_t st) {
+                       const uint32_t* lut_idx, const OutDest& out_big, const int32_t* out_idx, int count, int sm_count, cudaStream_t st) {
     if (count <= 0) return;
 #define FSC_STREAM(ACC, CTS, NH) \
     launch_pbs_stream_t<ACC, CTS, NH>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st)

@@ -2,6 +2,7 @@
 // every CTA of pbs_stream_kernel / pbs_split_kernel copies into shared memory.
 #pragma once
 #include <cuda_runtime.h>
+#include <mutex>
 #include <vector>
 #include "pbs_core2.cuh"
 #include "fsc_internal.h"
@@ -17,8 +18,10 @@ constexpr int kTabU0 = 0, kTabU2 = 16, kTabL1 = 32, kTabL3 = 544, kTabTwist = 10
 template <typename AccT>
 const cplx* stream_tables() {      // device pointer, built once per device and accumulator type
     static cplx* per_dev[64] = {};
+    static std::mutex mu;      // contexts of different host threads may reach this together
     int dev = 0;
     FSC_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
     cplx*& d = per_dev[dev & 63];
     if (!d) {
         std::vector<cplx> h(kTabCplx);

@@ -1,6 +1,7 @@
 // radix.cpp — radix-integer operators as sequences of batched PBS levels (see radix.h).
 #include "radix.h"
 
+#include <limits.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -27,11 +28,19 @@ static void drop_zero_terms(Block& b) {
                   b.terms.end());
 }
 
+// variance of a linear combination of independent slots, from the merged coefficients
+static int32_t variance_of(const Block& b) {
+    int64_t v = 0;
+    for (const auto& e : b.terms) v += (int64_t)e.second * e.second * e.first->nv;
+    return (int32_t)std::min<int64_t>(v, INT32_MAX);
+}
+
 Block operator+(const Block& a, const Block& b) {
     Block r = a;
     for (const auto& e : b.terms) merge_term(r.terms, e.first, e.second);
     drop_zero_terms(r);
-    r.cst += b.cst; r.deg += b.deg; r.nl += b.nl; r.nv += b.nv;
+    r.cst += b.cst; r.deg += b.deg; r.nl += b.nl;
+    r.nv = variance_of(r);
     return r;
 }
 Block operator*(const Block& a, int c) {
@@ -39,7 +48,8 @@ Block operator*(const Block& a, int c) {
     Block r = a;
     for (auto& e : r.terms) e.second *= c;
     drop_zero_terms(r);
-    r.cst *= c; r.deg *= c; r.nl *= c; r.nv *= c * c;
+    r.cst *= c; r.deg *= c; r.nl *= c;
+    r.nv = variance_of(r);
     return r;
 }
 Block complement(const Block& a, int top) {
@@ -131,6 +141,7 @@ void Evaluator::materialize(Radix& r) {
         q.cst = b.cst;
         q.dst = be_->alloc_slot();
         Block nb = Block::from_slot(std::make_shared<SlotRef>(be_, q.dst), b.deg, b.nl);
+        nb.terms[0].first->nv = std::max(b.nv, 1);      // the materialised slot carries the combination's variance
         nb.nv = b.nv;
         lin.push_back(std::move(q));
         // keep the sources alive until run_linear has been enqueued
@@ -179,7 +190,7 @@ Radix Evaluator::cast(const Radix& a, int n_blocks) {
 // Number of ranks a level of this evaluator may be cut over (1 without level sharding).
 int Evaluator::scan_world() const {
     const Exchange& x = be_->exchange;
-    return (x.world > 1 && x.all_gather) ? x.world : 1;
+    return x.enabled() ? x.world : 1;
 }
 
 // Radix-3 Hillis-Steele scan.  States are re-encoded as the digits of a binary adder, e = 0 (no carry), 1 (propagates),

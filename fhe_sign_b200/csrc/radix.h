@@ -70,8 +70,11 @@ struct Exchange {
     size_t capacity = 0;
     ExchangeFn all_gather = nullptr;
     void* user = nullptr;
-    bool active(size_t count) const { return world > 1 && all_gather && count >= min_width; }
+    bool peer = false;                  // fused exchange: the PBS epilogue stores into every rank's peer-mapped pool (fsc_peer_*)
+    bool enabled() const { return world > 1 && (all_gather || peer); }
+    bool active(size_t count) const { return enabled() && count >= min_width; }
 };
+constexpr size_t kPeerHandleBytes = 128;
 inline void shard_range(size_t count, int rank, int world, size_t* per, size_t* lo, size_t* hi) {
     *per = (count + world - 1) / world;
     *lo = std::min(count, (size_t)rank * *per);
@@ -93,6 +96,10 @@ public:
     virtual size_t words_per_block() const = 0;
     virtual void import_blocks(const uint64_t* host, size_t n, const int32_t* slots) = 0;
     virtual void export_blocks(const int32_t* slots, size_t n, uint64_t* host) = 0;
+    // peer-mapped block pools (CUDA backend only): see fsc_peer_pool_export / _connect in include/fhe_sign_cuda.h
+    virtual void peer_export(size_t, uint8_t*) { throw RadixError("peer-mapped pools need the CUDA backend"); }
+    virtual void peer_connect(int, int, size_t, const uint8_t*) { throw RadixError("peer-mapped pools need the CUDA backend"); }
+    virtual void peer_disconnect() {}
     // statistics
     uint64_t pbs_count = 0, level_count = 0;
 };
@@ -100,6 +107,7 @@ public:
 struct SlotRef {
     RadixBackend* be;
     int32_t idx;
+    int32_t nv = 1;                     // noise variance of the ciphertext in this slot, in units of one fresh PBS output
     SlotRef(RadixBackend* b, int32_t i) : be(b), idx(i) {}
     ~SlotRef() { be->free_slot(idx); }
     SlotRef(const SlotRef&) = delete;
@@ -114,7 +122,8 @@ struct Block {
     int32_t cst = 0;
     int32_t deg = 0;
     int32_t nl = 0;
-    int32_t nv = 0;                     // noise variance in units of one fresh PBS output (sum of squared coefficients)
+    int32_t nv = 0;                     // noise variance in units of one fresh PBS output: sum over DISTINCT slots of coef^2 * slot variance
+                                        // (recomputed from the merged coefficients: x + x is 4, not 2)
 
     bool trivial() const { return terms.empty(); }
     static Block constant(int v) { Block b; b.cst = v; b.deg = v; return b; }

@@ -241,4 +241,25 @@ fsc_status fsc_set_level_exchange(fsc_ctx* ctx, int32_t rank, int32_t world, siz
     RX_END(ctx)
 }
 
+fsc_status fsc_peer_pool_export(fsc_ctx* ctx, size_t capacity_blocks, uint8_t* handle_out) {
+    RX_BEGIN(ctx)
+    need(handle_out && capacity_blocks, "null handle buffer or zero capacity");
+    ctx->rb->peer_export(capacity_blocks, handle_out);
+    RX_END(ctx)
+}
+
+fsc_status fsc_peer_pool_connect(fsc_ctx* ctx, int32_t rank, int32_t world, size_t min_width, const uint8_t* handles) {
+    RX_BEGIN(ctx)
+    need(world >= 1 && world <= 8 && rank >= 0 && rank < world, "rank / world out of range (at most 8 GPUs of one node)");
+    need(handles, "null handle array");
+    ctx->rb->peer_connect(rank, world, min_width, handles);
+    RX_END(ctx)
+}
+
+fsc_status fsc_peer_pool_disconnect(fsc_ctx* ctx) {
+    RX_BEGIN(ctx)
+    ctx->rb->peer_disconnect();
+    RX_END(ctx)
+}
+
 }  // extern "C"

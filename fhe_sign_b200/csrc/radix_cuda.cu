@@ -3,8 +3,10 @@
 // inputs, one keyswitch launch, one PBS launch scattering its outputs into the pool.
 #include <cuda_runtime.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <map>
+#include <string>
 #include <vector>
 
 #include "engine.h"
@@ -27,6 +29,7 @@ public:
     ~CudaBackend() override {
         cudaSetDevice(eng->dev);
         cudaStreamSynchronize(eng->stream);
+        try { peer_disconnect(); } catch (...) {}
         if (pool) cudaFree(pool);
         if (luts.d) cudaFree(luts.d);
         if (stage_big) cudaFree(stage_big);
@@ -45,10 +48,18 @@ public:
     }
     void free_slot(int32_t s) override { free_list.push_back(s); }
 
+    // The allocation carries a 4 KB tail behind the slots: the flag words of the peer barrier (one IPC handle covers both).
+    static constexpr size_t kFlagTail = 4096;
+    uint64_t* flag_area() const { return pool + cap * words; }      // [0, 8): arrivals per rank; [8]: barrier timeout record
     void grow_pool(size_t new_cap) {
+        if (peer_fixed) throw Error(FSC_ERR_OOM, "block pool exhausted: a peer-mapped pool cannot grow past the capacity given to fsc_peer_pool_export");
         eng->use();
         uint64_t* np = nullptr;
-        FSC_CUDA_CHECK(cudaMalloc(&np, new_cap * words * 8));
+        FSC_CUDA_CHECK(cudaMalloc(&np, new_cap * words * 8 + kFlagTail));
+        {
+            const cudaError_t e = cudaMemsetAsync(np + new_cap * words, 0, kFlagTail, eng->stream);
+            if (e != cudaSuccess) { cudaFree(np); FSC_CUDA_CHECK(e); }
+        }
         if (pool) {
             cudaError_t e = cudaMemcpyAsync(np, pool, next * words * 8, cudaMemcpyDeviceToDevice, eng->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(eng->stream);
@@ -169,7 +180,11 @@ public:
     void run_level(const std::vector<LevelReq>& reqs) override {
         if (reqs.empty()) return;
         eng->use();
-        if (exchange.active(reqs.size())) { run_level_sharded(reqs); return; }
+        if (exchange.active(reqs.size())) {
+            if (exchange.peer) run_level_peer(reqs); else run_level_sharded(reqs);
+            return;
+        }
+        peer_dirty = true;      // local work since the last barrier: a peer must not overwrite slots this level may still read
         ensure_stage_big(reqs.size());
         eng->ensure_scratch(reqs.size());
         const Csr c = upload(reqs, true);
@@ -203,9 +218,124 @@ public:
         FSC_CUDA_CHECK(cudaGetLastError());
         ++sharded_levels;
     }
+    // ---- fused exchange over peer-mapped pools ---------------------------------------------------------------
+    // Rank r bootstraps its contiguous slice; the kernel's sample-extraction epilogue stores every output word into the
+    // destination slot of EVERY rank's pool (own + peers over NVLink), so the next level finds its inputs in place.
+    //   barrier A (only if this rank did local-only work since the last barrier): every rank has finished all earlier
+    //              kernels, so no rank still reads a slot that a faster peer is about to overwrite;
+    //   lincomb + keyswitch + blind rotation of the slice (destinations: all pools);
+    //   barrier B: every rank's slice has landed in this rank's pool.
+    void peer_barrier() {
+        launch_peer_barrier(peer_flags, flag_area() + 8, exchange.rank, exchange.world, ++peer_seq, eng->stream);
+        ++eng->launches;
+        FSC_CUDA_CHECK(cudaGetLastError());
+    }
+    void run_level_peer(const std::vector<LevelReq>& reqs) {
+        size_t per, lo, hi;
+        shard_range(reqs.size(), exchange.rank, exchange.world, &per, &lo, &hi);
+        const size_t mine = hi - lo;
+        ensure_stage_big(std::max<size_t>(mine, 1));
+        eng->ensure_scratch(std::max<size_t>(mine, 1));
+        const Csr c = upload(reqs, true);
+        if (peer_dirty) peer_barrier();
+        if (mine) {
+            launch_lincomb(pool, c.row_ptr + lo, c.slot, c.coef, c.cst + lo, delta, stage_big, nullptr, (int)mine, (int)words, eng->stream);
+            ++eng->launches;
+            FSC_CUDA_CHECK(cudaGetLastError());
+            eng->keyswitch(stage_big, eng->scratch_small, mine);
+            eng->pbs(eng->scratch_small, &luts, c.lut + lo, pool, mine, c.dst + lo, &peer_dests);
+        }
+        peer_barrier();
+        peer_dirty = false;
+        ++sharded_levels;
+    }
+    void check_peer_error() {
+        if (!exchange.peer) return;
+        uint64_t bad = 0;
+        FSC_CUDA_CHECK(cudaMemcpyAsync(&bad, flag_area() + 8, 8, cudaMemcpyDeviceToHost, eng->stream));
+        FSC_CUDA_CHECK(cudaStreamSynchronize(eng->stream));
+        if (bad) throw Error(FSC_ERR_COMM, "level exchange: a peer did not reach barrier " + std::to_string(bad) + " in time (ranks out of step, or a rank died)");
+    }
+
+    struct PeerHandle {                  // the 128 opaque bytes of fsc_peer_pool_export
+        cudaIpcMemHandle_t ipc;          // 64 bytes
+        uint64_t pid, ptr, capacity, words;
+        int32_t device, pad;
+    };
+    static_assert(sizeof(PeerHandle) <= kPeerHandleBytes, "peer handle blob");
+
+    void peer_export(size_t capacity_blocks, uint8_t* out) override {
+        eng->use();
+        if (exchange.peer) throw Error(FSC_ERR_BAD_ARG, "peer pool already connected");
+        FSC_CUDA_CHECK(cudaStreamSynchronize(eng->stream));
+        peer_fixed = false;
+        if (cap < capacity_blocks) grow_pool(capacity_blocks);      // keeps the blocks already imported
+        FSC_CUDA_CHECK(cudaStreamSynchronize(eng->stream));
+        peer_fixed = true;
+        PeerHandle h;
+        memset(&h, 0, sizeof(h));
+        FSC_CUDA_CHECK(cudaIpcGetMemHandle(&h.ipc, pool));
+        h.pid = (uint64_t)getpid(); h.ptr = (uint64_t)(uintptr_t)pool; h.capacity = cap; h.words = words; h.device = eng->dev;
+        memset(out, 0, kPeerHandleBytes);
+        memcpy(out, &h, sizeof(h));
+    }
+    void peer_connect(int rank, int world, size_t min_width, const uint8_t* handles) override {
+        eng->use();
+        if (!peer_fixed) throw Error(FSC_ERR_BAD_ARG, "call fsc_peer_pool_export before fsc_peer_pool_connect");
+        if (exchange.peer) throw Error(FSC_ERR_BAD_ARG, "peer pool already connected");
+        if (world > kMaxPeers) throw Error(FSC_ERR_BAD_ARG, "at most 8 ranks");
+        FSC_CUDA_CHECK(cudaStreamSynchronize(eng->stream));
+        uint64_t* pools[kMaxPeers] = {};
+        for (int q = 0; q < world; ++q) {
+            PeerHandle h;
+            memcpy(&h, handles + (size_t)q * kPeerHandleBytes, sizeof(h));
+            if (h.capacity != cap || h.words != words) throw Error(FSC_ERR_BAD_ARG, "peer pools must have the same capacity and block size on every rank");
+            if (q == rank) {
+                if (h.ptr != (uint64_t)(uintptr_t)pool) throw Error(FSC_ERR_BAD_ARG, "handle at index `rank` is not this context's own");
+                pools[q] = pool;
+            } else if (h.pid == (uint64_t)getpid()) {      // another context of this process: plain peer access
+                int can = 0;
+                FSC_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, eng->dev, h.device));
+                if (!can) throw Error(FSC_ERR_COMM, "no peer access between the two devices");
+                const cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) FSC_CUDA_CHECK(e);
+                (void)cudaGetLastError();
+                pools[q] = reinterpret_cast<uint64_t*>((uintptr_t)h.ptr);
+            } else {
+                void* p = nullptr;
+                const cudaError_t e = cudaIpcOpenMemHandle(&p, h.ipc, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) {
+                    for (void* o : peer_opened) cudaIpcCloseMemHandle(o);
+                    peer_opened.clear();
+                    throw Error(FSC_ERR_COMM, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+                }
+                peer_opened.push_back(p);
+                pools[q] = static_cast<uint64_t*>(p);
+            }
+        }
+        // destination 0 is the local pool; the peers follow in ring order from this rank so that simultaneous epilogues
+        // spread over different NVLink targets
+        for (int i = 0; i < kMaxPeers; ++i) { peer_dests.base[i] = nullptr; peer_flags[i] = nullptr; }
+        peer_dests.n = world;
+        for (int i = 0; i < world; ++i) peer_dests.base[i] = pools[(rank + i) % world];
+        for (int q = 0; q < world; ++q) peer_flags[q] = pools[q] + cap * words;
+        exchange.rank = rank; exchange.world = world; exchange.min_width = min_width;
+        exchange.all_gather = nullptr; exchange.buffer = nullptr; exchange.capacity = 0; exchange.peer = world > 1;
+        peer_seq = 0; peer_dirty = true;
+    }
+    void peer_disconnect() override {
+        if (!exchange.peer && peer_opened.empty()) { return; }
+        eng->use();
+        cudaStreamSynchronize(eng->stream);
+        for (void* o : peer_opened) cudaIpcCloseMemHandle(o);
+        peer_opened.clear();
+        exchange = Exchange();
+    }
+
     void run_linear(const std::vector<LinReq>& reqs) override {
         if (reqs.empty()) return;
         eng->use();
+        peer_dirty = true;
         const Csr c = upload(reqs, false);
         launch_lincomb(pool, c.row_ptr, c.slot, c.coef, c.cst, delta, pool, c.dst, (int)c.count, (int)words, eng->stream);
         ++eng->launches;
@@ -214,17 +344,39 @@ public:
 
     // ---- host transfer -----------------------------------------------------------------------------
     size_t words_per_block() const override { return words; }
+    // One contiguous copy + one scatter / gather launch per radix value instead of one cudaMemcpyAsync per block
+    // (a signature moves 385 blocks in and 272 out).
+    const int32_t* upload_indices(const int32_t* idx, size_t n) {
+        char* h = acquire_pinned(n * 4);
+        ensure_dev_idx(n * 4);
+        memcpy(h, idx, n * 4);
+        FSC_CUDA_CHECK(cudaMemcpyAsync(dev_idx, h, n * 4, cudaMemcpyHostToDevice, eng->stream));
+        FSC_CUDA_CHECK(cudaEventRecord(stage_ev[cur], eng->stream));
+        return reinterpret_cast<const int32_t*>(dev_idx);
+    }
     void import_blocks(const uint64_t* host, size_t n, const int32_t* slots) override {
+        if (!n) return;
         eng->use();
-        for (size_t i = 0; i < n; ++i)
-            FSC_CUDA_CHECK(cudaMemcpyAsync(pool + (size_t)slots[i] * words, host + i * words, words * 8, cudaMemcpyHostToDevice, eng->stream));
-        FSC_CUDA_CHECK(cudaStreamSynchronize(eng->stream));
+        ensure_stage_big(n);
+        FSC_CUDA_CHECK(cudaMemcpyAsync(stage_big, host, n * words * 8, cudaMemcpyHostToDevice, eng->stream));
+        const int32_t* d = upload_indices(slots, n);
+        launch_scatter(stage_big, d, pool, (int)n, (int)words, eng->stream);
+        ++eng->launches;
+        FSC_CUDA_CHECK(cudaGetLastError());
+        FSC_CUDA_CHECK(cudaStreamSynchronize(eng->stream));      // the caller may release `host` on return
+        peer_dirty = true;
     }
     void export_blocks(const int32_t* slots, size_t n, uint64_t* host) override {
+        if (!n) return;
         eng->use();
-        for (size_t i = 0; i < n; ++i)
-            FSC_CUDA_CHECK(cudaMemcpyAsync(host + i * words, pool + (size_t)slots[i] * words, words * 8, cudaMemcpyDeviceToHost, eng->stream));
+        ensure_stage_big(n);
+        const int32_t* d = upload_indices(slots, n);
+        launch_gather(pool, d, stage_big, (int)n, (int)words, eng->stream);
+        ++eng->launches;
+        FSC_CUDA_CHECK(cudaGetLastError());
+        FSC_CUDA_CHECK(cudaMemcpyAsync(host, stage_big, n * words * 8, cudaMemcpyDeviceToHost, eng->stream));
         FSC_CUDA_CHECK(cudaStreamSynchronize(eng->stream));
+        check_peer_error();
     }
 
 private:
@@ -245,6 +397,13 @@ private:
     size_t pinned_cap[kStages] = {0, 0, 0, 0};
     cudaEvent_t stage_ev[kStages] = {nullptr, nullptr, nullptr, nullptr};
     int cur = 0;
+    // peer-mapped pools (level sharding with the exchange fused into the blind rotation)
+    bool peer_fixed = false;             // capacity frozen by fsc_peer_pool_export
+    bool peer_dirty = true;              // local-only work enqueued since the last barrier
+    uint64_t peer_seq = 0;               // barrier counter (identical on every rank: SPMD)
+    OutDest peer_dests{};                // [0] own pool, then the peers' pools
+    uint64_t* peer_flags[kMaxPeers] = {};
+    std::vector<void*> peer_opened;      // cudaIpcOpenMemHandle mappings to close
 };
 
 }  // namespace

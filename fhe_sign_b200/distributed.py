@@ -1,4 +1,12 @@
-"""Multi-GPU level sharding: one process per GPU, replicated keys, NCCL all-gather of PBS level outputs.
+"""Multi-GPU level sharding: one process per GPU, replicated keys.
+
+Two exchange paths behind the same radix operators:
+  * `enable_peer_sharding` (default of bench.py / the tools): the library's own exchange - every rank's block pool is
+    mapped into its peers (CUDA IPC) and the blind rotation's epilogue stores its outputs straight into every pool over
+    NVLink (fsc_peer_pool_export / fsc_peer_pool_connect).  Python is only involved in swapping the 128-byte handles at
+    set-up; nothing of it runs in the level loop.
+  * `enable_level_sharding`: the callback form - an NCCL all-gather of PBS level outputs enqueued by a Python callback
+    (kept as the baseline the fused path is measured against, and for the gloo CPU tests).
 
 `enable_level_sharding(ctx, ...)` allocates the exchange buffer as a torch tensor on the context's device and
 installs an all-gather callback (fsc_set_level_exchange) that runs `torch.distributed.all_gather_into_tensor`
@@ -61,3 +69,40 @@ def enable_level_sharding(ctx, stream, min_width=149, capacity_blocks=1 << 16, g
     ctx._check(rc)
     ctx._exchange_keepalive = (buf, cb)      # the library keeps raw pointers to both
     return buf
+
+
+PEER_HANDLE_BYTES = 128
+
+
+def enable_peer_sharding(ctx, min_width=149, capacity_blocks=1 << 17, group=None):
+    """Library-owned exchange over peer-mapped block pools (include/fhe_sign_cuda.h, fsc_peer_*).
+
+    Every rank exports its pool handle, the handles are all-gathered once through torch.distributed (any host channel
+    would do), every rank connects.  From then on a sharded level is: lincomb + keyswitch + blind rotation whose epilogue
+    writes into all pools + one flag-barrier kernel - no callback, no NCCL, no Python."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mine = (C.c_uint8 * PEER_HANDLE_BYTES)()
+    ctx._check(ctx.L.fsc_peer_pool_export(ctx.h, capacity_blocks, mine))
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t_mine = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=dev)
+    t_all = torch.empty(world * PEER_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+    if dev == "cuda":
+        dist.all_gather_into_tensor(t_all, t_mine, group=group)
+    else:
+        parts = [torch.empty(PEER_HANDLE_BYTES, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(parts, t_mine, group=group)
+        t_all = torch.cat(parts)
+    blob = bytes(t_all.cpu().numpy().tobytes())
+    handles = (C.c_uint8 * (world * PEER_HANDLE_BYTES)).from_buffer_copy(blob)
+    ctx._check(ctx.L.fsc_peer_pool_connect(ctx.h, rank, world, min_width, handles))
+    dist.barrier(group=group)      # nobody starts storing into a pool that a slower rank has not mapped yet (set-up only)
+
+
+def disable_peer_sharding(ctx, group=None):
+    import torch.distributed as dist
+    ctx.sync()
+    dist.barrier(group=group)      # every rank is done writing into every pool
+    ctx._check(ctx.L.fsc_peer_pool_disconnect(ctx.h))

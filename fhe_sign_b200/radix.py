@@ -12,7 +12,8 @@ WORDS = 2049
 RADIX_EXPORTS = ["fsc_radix_from_lwe", "fsc_radix_to_lwe", "fsc_radix_trivial", "fsc_radix_clone", "fsc_radix_free",
                  "fsc_radix_len", "fsc_radix_binary", "fsc_radix_scalar", "fsc_radix_mul_wide", "fsc_radix_mul_add_wide", "fsc_radix_cast",
                  "fsc_radix_slice", "fsc_radix_concat", "fsc_radix_sum", "fsc_radix_select", "fsc_radix_stats",
-                 "fsc_radix_stats2", "fsc_set_level_exchange"]
+                 "fsc_radix_stats2", "fsc_set_level_exchange", "fsc_peer_pool_export", "fsc_peer_pool_connect",
+                 "fsc_peer_pool_disconnect"]
 
 
 def declare(L):
@@ -29,6 +30,8 @@ def declare(L):
         "fsc_radix_select": [vp, vp, vp, vp, pp], "fsc_radix_stats": [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
         "fsc_radix_stats2": [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
         "fsc_set_level_exchange": [vp, C.c_int32, C.c_int32, sz, vp, sz, vp, vp],
+        "fsc_peer_pool_export": [vp, sz, vp], "fsc_peer_pool_connect": [vp, C.c_int32, C.c_int32, sz, vp],
+        "fsc_peer_pool_disconnect": [vp],
     }
     for name, args in sig.items():
         f = getattr(L, name)

@@ -39,7 +39,7 @@ enum {
     FSC_ERR_OOM = 3,         /* device or host allocation failed                                */
     FSC_ERR_CUDA = 4,        /* CUDA runtime error / no device                                  */
     FSC_ERR_NO_KEYS = 5,     /* server keys not uploaded yet                                    */
-    FSC_ERR_COMM = 6,        /* level-exchange callback failed (multi-GPU)                      */
+    FSC_ERR_COMM = 6,        /* level exchange failed: callback error or a peer missed the barrier */
     FSC_ERR_INTERNAL = 7
 };
 
@@ -177,14 +177,32 @@ fsc_status fsc_radix_select(fsc_ctx *ctx, const fsc_radix *cond, const fsc_radix
 typedef int32_t (*fsc_exchange_fn)(void *user, void *buffer, size_t bytes_per_rank);
 fsc_status fsc_set_level_exchange(fsc_ctx *ctx, int32_t rank, int32_t world, size_t min_width, void *buffer,
                                   size_t capacity_bytes, fsc_exchange_fn all_gather, void *user);
+/* The same sharding with the exchange OWNED BY THE LIBRARY and fused into the blind-rotation kernel (no callback, no
+ * NCCL, nothing but these three calls for a Rust host): every rank's block pool is a fixed-capacity allocation mapped
+ * into its peers (CUDA IPC between processes, cudaDeviceEnablePeerAccess inside one process); the sample-extraction
+ * epilogue of rank r's slice stores each output word straight into the destination slot of EVERY rank's pool over
+ * NVLink, and a flag barrier in peer memory (one tiny kernel; st.release.sys / ld.acquire.sys, bounded spin) orders the
+ * levels.  No staging buffer, no all-gather, no scatter launch.
+ *   1. every rank: fsc_peer_pool_export(ctx, capacity_blocks, handle)       -> 128 opaque bytes
+ *   2. the host exchanges the `world` handles by any means (a file, a socket, torch.distributed ...)
+ *   3. every rank: fsc_peer_pool_connect(ctx, rank, world, min_width, all_handles)   (handles in rank order)
+ * Contract as above: SPMD (identical operator sequence and identical input ciphertexts on every rank), keys
+ * replicated; the pool cannot grow past capacity_blocks once exported (FSC_ERR_OOM).  A peer that never arrives
+ * makes the barrier give up after a few seconds; the next download reports FSC_ERR_COMM.                       */
+#define FSC_PEER_HANDLE_BYTES 128
+fsc_status fsc_peer_pool_export(fsc_ctx *ctx, size_t capacity_blocks, uint8_t *handle_out);
+fsc_status fsc_peer_pool_connect(fsc_ctx *ctx, int32_t rank, int32_t world, size_t min_width, const uint8_t *handles);
+fsc_status fsc_peer_pool_disconnect(fsc_ctx *ctx);
 /* bootstraps, PBS levels and sharded levels issued by the radix layer so far on this context     */
 fsc_status fsc_radix_stats2(const fsc_ctx *ctx, uint64_t *pbs_count, uint64_t *level_count, uint64_t *sharded_levels);
 /* bootstraps and PBS levels issued by the radix layer so far on this context                      */
 fsc_status fsc_radix_stats(const fsc_ctx *ctx, uint64_t *pbs_count, uint64_t *level_count);
 
 /* ---- client side (host CPU): key generation, block encryption, decryption ------------------- */
-/* Replaces tfhe::generate_keys / FheUintN::try_encrypt / decrypt (src/biguint.rs:26,70,277).  Plain host code;
- * randomness is a ChaCha20 stream keyed by `seed` (deterministic for reproducible tests).                  */
+/* Replaces tfhe::generate_keys / FheUintN::try_encrypt / decrypt (src/biguint.rs:26,70,277).  Plain host code.
+ * Randomness: ChaCha20 under a 256-bit master key from the OS CSPRNG (getrandom; the reference's tfhe is built with
+ * seeder_unix, Cargo.toml:9) for the keys, and under a second OS-drawn 256-bit key per client instance for
+ * encryption masks and noise - never derived from a caller seed, a counter or anything persisted.          */
 enum { FSC_NOISE_GAUSSIAN = 0, FSC_NOISE_TUNIFORM = 1 };
 typedef struct {
     uint32_t noise_kind;            /* FSC_NOISE_GAUSSIAN: standard deviations below (fractions of q)          */
@@ -195,7 +213,12 @@ typedef struct {
     double glwe_noise_std;
 } fsc_noise_params;
 typedef struct fsc_client fsc_client;
-fsc_status fsc_client_keygen(const fsc_params *params, const fsc_noise_params *noise, uint64_t seed, fsc_client **out);
+fsc_status fsc_client_keygen(const fsc_params *params, const fsc_noise_params *noise, fsc_client **out);
+/* TEST-ONLY deterministic variant: the master key is expanded from a 64-bit seed (at most 64 bits of entropy, anyone
+ * who knows the seed re-derives the secret key).  Encryption randomness is still fresh OS entropy ...           */
+fsc_status fsc_client_keygen_seeded(const fsc_params *params, const fsc_noise_params *noise, uint64_t seed, fsc_client **out);
+/* ... unless a test pins it too (reproducible ciphertexts, e.g. identical inputs on every rank of a multi-GPU run). */
+fsc_status fsc_client_set_encryption_seed(fsc_client *c, uint64_t seed);
 fsc_status fsc_client_free(fsc_client *c);
 const char *fsc_client_last_error(const fsc_client *c);
 /* server key material for fsc_keys_upload; the pointers stay valid until fsc_client_free            */
@@ -209,8 +232,9 @@ fsc_status fsc_client_decrypt_blocks(fsc_client *c, const uint64_t *blocks, size
 
 /* ---- on-disk formats (host CPU; container layout documented in csrc/keyfile.cpp and INTEGRATION.md) ----
  * Replaces nothing in the reference, which regenerates keys in every test (src/biguint.rs:277); a deployment keeps
- * the client key (parameters + noise + seed + secret bits, a few KB: the 123 MB of server key material are re-derived
- * from the seed on load) on the signer's side and ships the expanded server key, without secrets, to the GPU host. */
+ * the client key (parameters + noise + 256-bit master key + secret bits, a few KB: the 123 MB of server key material are
+ * re-derived from the master key on load; no encryption state is stored) on the signer's side and ships the expanded
+ * server key, without secrets, to the GPU host.  The checksum detects corruption; it is not an authenticator.   */
 fsc_status fsc_client_save(const fsc_client *c, const char *path);
 fsc_status fsc_client_load(const char *path, fsc_client **out);
 fsc_status fsc_server_keys_save(const fsc_client *c, const char *path);

@@ -29,6 +29,53 @@ def test_keygen_is_seeded(ck):
     assert not np.array_equal(b.server_keys()[1], ck.server_keys()[1])
 
 
+def test_default_keygen_draws_os_entropy():
+    """the default key must not be re-derivable - two default clients differ, and each works."""
+    a, b = ClientKey("toy"), ClientKey("toy")
+    assert not np.array_equal(a.secret_keys()[0], b.secret_keys()[0])
+    assert not np.array_equal(a.secret_keys()[1], b.secret_keys()[1])
+    vals = np.arange(16, dtype=np.uint8)
+    assert (a.decrypt_block_values(a.encrypt_block_values(vals)) == vals).all()
+    assert 300 < int(a.secret_keys()[1].sum()) < 1748            # a binary key of 2048 bits, not a constant
+
+
+def test_encryption_randomness_is_per_instance_even_with_the_same_key_seed():
+    """encryption masks never come from (seed, counter): two instances with the same test seed (or one
+    key file loaded twice) must not emit the same mask, or b1 - b2 would leak delta * (m1 - m2)."""
+    a, b = ClientKey("toy", seed=9), ClientKey("toy", seed=9)
+    vals = np.arange(8, dtype=np.uint8)
+    ca, cb = a.encrypt_block_values(vals), b.encrypt_block_values(vals)
+    assert not np.array_equal(ca[:, :2048], cb[:, :2048])
+    assert (b.decrypt_block_values(ca) == vals).all()            # same secret key
+    # the explicit test hook pins it (reproducible ciphertexts for multi-rank tests)
+    c, d = ClientKey("toy", seed=9, encryption_seed=3), ClientKey("toy", seed=9, encryption_seed=3)
+    assert np.array_equal(c.encrypt_block_values(vals), d.encrypt_block_values(vals))
+
+
+def test_key_file_header_is_range_checked(ck, tmp_path):
+    """base_log * level and the tuniform bound feed shifts - a crafted header is refused."""
+    import struct
+    from fhe_sign_b200.capi import FscError
+    path = tmp_path / "client.fsc"
+    ck.save(path)
+    raw = bytearray(path.read_bytes())
+
+    def refused(offset, value):
+        bad = bytearray(raw)
+        bad[offset:offset + 4] = struct.pack("<I", value)
+        body = bytes(bad[:-8])
+        h = 14695981039346656037
+        for byte in body:
+            h = ((h ^ byte) * 1099511628211) & (2**64 - 1)
+        (tmp_path / "crafted.fsc").write_bytes(body + struct.pack("<Q", h))      # checksum fixed up: only the range check can refuse it
+        with pytest.raises(FscError, match="header|parameter"):
+            ClientKey.load(tmp_path / "crafted.fsc")
+
+    refused(16 + 4 * 3, 64)          # pbs_base_log 64: the 64 - base_log * level shift would be undefined
+    refused(16 + 4 * 4, 1 << 30)     # pbs_level huge: base_log * level overflows u32
+    refused(56 + 4, 200)             # lwe_tuniform_bound (only read for the tuniform kind, still range-checked there)
+
+
 def test_keyswitching_key_rows_encrypt_the_big_key_bits(ck):
     lwe, glwe = ck.secret_keys()
     _, ksk = ck.server_keys()
@@ -68,13 +115,13 @@ def test_bootstrapping_key_rows_encrypt_the_small_key_bits(ck, orc):
 # ---- on-disk formats (csrc/keyfile.cpp) ----
 
 def test_client_key_file_roundtrip(ck, tmp_path):
-    """the seeded client key file re-derives the same secret and server keys and never replays encryption randomness."""
+    """the client key file re-derives the same secret and server keys and never replays encryption randomness."""
     from fhe_sign_b200.client import ClientKey
     vals = np.arange(16, dtype=np.uint8)
     ct_before = ck.encrypt_block_values(vals)
     path = tmp_path / "client.fsc"
     ck.save(path)
-    assert path.stat().st_size < 64 * 1024                       # parameters + seed + secret bits, not 123 MB
+    assert path.stat().st_size < 64 * 1024                       # parameters + master key + secret bits, not 123 MB
     ck2 = ClientKey.load(path)
     assert ck2.params.lwe_dim == ck.params.lwe_dim and ck2.params.pbs_base_log == ck.params.pbs_base_log
     for a, b in zip(ck.secret_keys(), ck2.secret_keys()):
@@ -84,7 +131,9 @@ def test_client_key_file_roundtrip(ck, tmp_path):
     assert (ck2.decrypt_block_values(ct_before) == vals).all()   # old ciphertexts decrypt under the loaded key
     ct_after = ck2.encrypt_block_values(vals)
     assert (ck.decrypt_block_values(ct_after) == vals).all()
-    assert not np.array_equal(ct_after, ct_before)               # the encryption counter travelled with the file
+    assert not np.array_equal(ct_after, ct_before)               # fresh OS entropy per instance, nothing persisted
+    ck3 = ClientKey.load(path)                                   # the same file loaded twice: still no shared masks
+    assert not np.array_equal(ck3.encrypt_block_values(vals)[:, :2048], ct_after[:, :2048])
 
 
 def test_server_key_and_block_files_roundtrip_and_reject_corruption(ck, tmp_path):
