@@ -616,6 +616,14 @@ void orc_negacyclic_mul_exact(uint32_t N, const uint64_t *a, const int64_t *b, u
     }
 }
 
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);      /* launchers such as torchrun export OMP_NUM_THREADS=1 */
+#else
+    (void)n;
+#endif
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

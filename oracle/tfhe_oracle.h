@@ -110,6 +110,8 @@ void orc_negacyclic_mul_fft(uint32_t N, const uint64_t *a, const int64_t *b, uin
 /* Exact schoolbook negacyclic product mod 2^64 (ground truth for the FFT hooks).         */
 void orc_negacyclic_mul_exact(uint32_t N, const uint64_t *a, const int64_t *b, uint64_t *c);
 int  orc_max_threads(void);
+/* Overrides OMP_NUM_THREADS for every later call (bench.py under torchrun, which exports OMP_NUM_THREADS=1). */
+void orc_set_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -28,9 +28,10 @@ class Client:
         return sum(int(v) << (2 * i) for i, v in enumerate(d))
 
 
-@pytest.fixture(scope="module")
-def cl(gpu_ctx, oracle_keys):
-    ctx = gpu_ctx(PRESET, 64)
+@pytest.fixture(scope="module", params=[32, 64], ids=["acc32", "acc64"])
+def cl(request, gpu_ctx, oracle_keys):
+    """every operator test runs at the product's default accumulator width (32) and at the reference's (64)"""
+    ctx = gpu_ctx(PRESET, request.param)
     return Client(oracle_keys(PRESET), ctx.radix)
 
 
@@ -113,3 +114,34 @@ def test_k_plus_ed_fused_and_reduced_mod_n(cl):
     a = cl.enc(x, 16)
     assert cl.dec(a // 5) == x // 5
     assert cl.dec(a % (2**32 - 5)) == x % (2**32 - 5)
+
+
+def test_256_bit_shift_min_div_at_128_blocks(cl):
+    """BASELINE configs[2] / [3] at their named width: the src/perf_test.rs:36,44,54 operators (>> by an encrypted amount,
+    min, / 5) on 256-bit values = 128 radix blocks, checked by decryption."""
+    rnd = random.Random(14)
+    M = 2**256 - 1
+    x, y = rnd.getrandbits(256), rnd.getrandbits(256)
+    a, b = cl.enc(x, 128), cl.enc(y, 128)
+    assert cl.dec(a >> b) == x >> (y % 256)                          # amount taken modulo the width (src/biguint.rs:469-499 rule)
+    amt = cl.enc(77, 128)
+    assert cl.dec(a >> amt) == x >> 77
+    assert cl.dec(a << amt) == (x << 77) & M
+    assert cl.dec(cl.api.min(a, b)) == min(x, y)
+    assert cl.dec(cl.api.max(a, b)) == max(x, y)
+    near = cl.enc(x ^ 1, 128)                                        # operands that differ in the last bit only
+    assert cl.dec(cl.api.min(a, near)) == min(x, x ^ 1)
+    assert cl.dec(a // 5) == x // 5
+    assert cl.dec(a % 5) == x % 5
+    assert cl.dec(cl.enc(M, 128) // 5) == M // 5                     # all-ones dividend: every carry chain at full length
+
+
+def test_256_bit_add_sub_mul_wrapping(cl):
+    rnd = random.Random(15)
+    M = 2**256
+    x, y = rnd.getrandbits(256), rnd.getrandbits(256)
+    a, b = cl.enc(x, 128), cl.enc(y, 128)
+    assert cl.dec(a + b) == (x + y) % M
+    assert cl.dec(a - b) == (x - y) % M
+    assert cl.dec(a * b) == (x * y) % M
+    assert cl.dec(cl.enc(M - 1, 128) + cl.enc(1, 128)) == 0          # the longest carry chain

@@ -17,11 +17,19 @@ GOLDEN = json.load(open(os.path.join(HERE, "golden", "schnorr_vectors.json")))
 F = 0xFFFFFFFF
 
 
-@pytest.fixture(scope="module")
-def ck(gpu_ctx, oracle_keys):
-    ctx = gpu_ctx("2_2_gaussian", 64)
-    bg.set_server_key(ctx)
-    return OracleClientKey(oracle_keys("2_2_gaussian"))
+@pytest.fixture(scope="module", params=[32, 64], ids=["acc32", "acc64"])
+def ck(request, gpu_ctx, oracle_keys):
+    """the whole signing suite at the product's default accumulator width (32) and at the reference's (64)"""
+    client = OracleClientKey(oracle_keys("2_2_gaussian"))
+    client.ctx = gpu_ctx("2_2_gaussian", request.param)
+    return client
+
+
+@pytest.fixture(autouse=True)
+def _install_server_key(request):
+    """tfhe::set_server_key before every test that uses `ck` (another test may have installed its own context)"""
+    if "ck" in request.fixturenames:
+        bg.set_server_key(request.getfixturevalue("ck").ctx)
 
 
 def test_biguint_kats_on_gpu(ck):
@@ -46,6 +54,23 @@ def test_sign_fhe_with_k0_vector0_faithful(ck):
     dt = time.perf_counter() - t0
     p1, l1 = bg._api().stats()
     print("faithful sign, vector 0: %.2f s, %d PBS in %d levels" % (dt, p1 - p0, l1 - l0))
+    assert sig.to_bytes().hex().upper() == v["reference_signature"] == v["csv_signature"].upper()
+
+
+def test_sign_fhe_with_k0_vector1_faithful_8x8_digits(ck, request):
+    """One full-width signature (8 x 8 digits: 64 iterations of src/biguint.rs:214-254, then the ripple Add of :123-191)
+    through the reference's own op-for-op schedule - every cast, every FheUint64 add / mul / >> 32 / & 0xFFFFFFFF and the
+    wrapping u32 add of :247-249 in the reference's order - on real ciphertexts."""
+    if "acc64" in request.node.name:
+        pytest.skip("the faithful 8 x 8 schedule runs once, at the default accumulator width")
+    v = GOLDEN[1]
+    d, k0, msg = int(v["secret_key"], 16), int(v["k0"], 16), bytes.fromhex(v["message"])
+    p0, l0 = bg._api().stats()
+    t0 = time.perf_counter()
+    sig = schnorr.sign_fhe_with_k0(msg, k0, d, BigUintFHE.new(d, ck), ck)
+    dt = time.perf_counter() - t0
+    p1, l1 = bg._api().stats()
+    print("faithful sign, vector 1 (8 x 8 digits): %.2f s, %d PBS in %d levels" % (dt, p1 - p0, l1 - l0))
     assert sig.to_bytes().hex().upper() == v["reference_signature"] == v["csv_signature"].upper()
 
 

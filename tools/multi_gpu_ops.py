@@ -1,8 +1,12 @@
 """256-bit radix operators with PBS levels sharded over the GPUs of one node (BASELINE configs[2..4]).
 Launch:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/multi_gpu_ops.py
-Every rank holds replicated keys and runs the same operator sequence; wide levels are sliced across ranks and
-completed by an NCCL all-gather (fhe_sign_b200/distributed.py).  Rank 0 checks decrypted results with the
-oracle client (seeded keys) and prints one JSON line per operator (time = max over ranks)."""
+             [--exchange peer|nccl] [--quick]
+Every rank holds replicated keys and runs the same operator sequence; wide levels are sliced across ranks.
+  --exchange peer (default): the library's own exchange - block pools mapped into every peer, the blind rotation's
+                  epilogue stores its outputs into all pools over NVLink, one flag-barrier kernel per level (fsc_peer_pool_*);
+  --exchange nccl: the callback form - NCCL all-gather enqueued from Python per level + a scatter kernel (baseline).
+Rank 0 checks decrypted results with the oracle client (seeded keys) and prints one JSON line per operator (time = max
+over ranks)."""
 import json
 import os
 import sys
@@ -16,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import fhe_sign_b200 as fsb
-from fhe_sign_b200.distributed import enable_level_sharding
+from fhe_sign_b200.distributed import enable_level_sharding, enable_peer_sharding
 from oracle import orc
 from oracle_client import OracleClientKey
 
@@ -25,6 +29,8 @@ N_ORDER = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
 
 def main():
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    exchange = sys.argv[sys.argv.index("--exchange") + 1] if "--exchange" in sys.argv else "peer"
+    quick = "--quick" in sys.argv
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -32,8 +38,12 @@ def main():
     stream = torch.cuda.Stream()
     ctx = fsb.Context(fsb.Params.preset("2_2_gaussian", acc_bits=32), device=local, stream=stream.cuda_stream)
     ctx.upload_keys(K.bsk, K.ksk)
+    min_width = int(os.environ.get("FSC_SHARD_MIN", "149"))
     if world > 1:
-        enable_level_sharding(ctx, stream, min_width=int(os.environ.get("FSC_SHARD_MIN", "149")), capacity_blocks=1 << 16)
+        if exchange == "peer":
+            enable_peer_sharding(ctx, min_width=min_width)
+        else:
+            enable_level_sharding(ctx, stream, min_width=min_width, capacity_blocks=1 << 16)
     R = ctx.radix
     ck = OracleClientKey(K, seed=77)          # same seed on every rank: identical ciphertexts everywhere
     rnd = np.random.default_rng(5)
@@ -47,8 +57,10 @@ def main():
         ("256-bit div 5", lambda: a // 5, x // 5),
         ("514-bit rem n", lambda: w % N_ORDER, (x * y + z) % N_ORDER),
     ]
+    if quick:
+        ops = ops[:2] + [("256-bit min", lambda: R.min(a, b), min(x, y))]
     for name, fn, want in ops:
-        for rep in range(2):
+        for rep in range(1 if quick else 2):
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
@@ -64,11 +76,13 @@ def main():
         got = ck.decrypt(out, R)
         ok = got == want
         if rank == 0:
-            print(json.dumps({"op": name, "n_gpus": world, "ms": round(float(t[0]) * 1e3, 2), "pbs": p1 - p0, "levels": l1 - l0,
-                              "sharded_levels": R.sharded_levels() - s0, "correct": bool(ok)}), flush=True)
+            print(json.dumps({"op": name, "n_gpus": world, "exchange": exchange if world > 1 else "none", "ms": round(float(t[0]) * 1e3, 2),
+                              "pbs": p1 - p0, "levels": l1 - l0, "sharded_levels": R.sharded_levels() - s0, "correct": bool(ok)}), flush=True)
         assert ok, (name, rank)
     if world > 1:
+        ctx.sync()
         dist.barrier()
+        ctx.close()
         dist.destroy_process_group()
 
 
