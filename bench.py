@@ -39,6 +39,7 @@ PRESET = os.environ.get("FSC_BENCH_PRESET", "2_2_gaussian")
 BATCH = int(os.environ.get("FSC_BENCH_BATCH", "4096"))
 ACC_BITS = int(os.environ.get("FSC_BENCH_ACC_BITS", "32"))
 WORKLOAD = "batched PBS microbench: %d LWE blocks, PARAM_MESSAGE_2_CARRY_2 (%s), keyswitch+PBS per block" % (BATCH, PRESET)
+_JSON_OUT = sys.stdout
 N_ORDER = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141        # src/scalar.rs:8
 FP64_NOMINAL_TF = 148 * 64 * 2 * 1.965e9 / 1e12      # 148 SMs x 64 FMA/clk x 2 x 1.965 GHz = 37.2
 
@@ -198,7 +199,7 @@ def run_reference(args, rank, world):
             line["cpu_baseline"]["ops"] = cpu_operator_times(K, threads, wide=True)
         except Exception as e:      # the baseline's operator leg must never cost the headline
             line["cpu_baseline"]["ops_error"] = repr(e)
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -371,6 +372,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # ONE JSON line on stdout: everything else any library prints there (NCCL's version banner, for one) goes to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -566,7 +573,7 @@ def main():
                 except Exception as e:
                     cpu["ops_error"] = repr(e)
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
