@@ -77,6 +77,7 @@ def load_library():
         "fsc_timer_stop": [vp, C.POINTER(C.c_float)],
         "fsc_launch_count": [vp, C.POINTER(C.c_uint64)],
         "fsc_debug_negacyclic_mul": [vp, vp, vp, vp, sz],
+        "fsc_debug_fourier_key": [vp, vp, i32],
         "fsc_measure_fp64_peak": [vp, C.POINTER(C.c_double)],
     }
     for name, args in sig.items():
@@ -95,7 +96,7 @@ EXPORTS = ["fsc_ctx_create", "fsc_ctx_destroy", "fsc_last_error", "fsc_get_param
            "fsc_lwe_alloc", "fsc_lwe_free", "fsc_lwe_upload", "fsc_lwe_download", "fsc_lwe_info",
            "fsc_luts_from_tables", "fsc_luts_upload", "fsc_luts_free", "fsc_keyswitch_batch", "fsc_pbs_batch",
            "fsc_ks_pbs_batch", "fsc_apply_lut_host", "fsc_timer_start", "fsc_timer_stop", "fsc_launch_count",
-           "fsc_debug_negacyclic_mul", "fsc_measure_fp64_peak", "fsc_pbs_kernel_name"]
+           "fsc_debug_negacyclic_mul", "fsc_debug_fourier_key", "fsc_measure_fp64_peak", "fsc_pbs_kernel_name"]
 from .radix import RADIX_EXPORTS  # noqa: E402
 EXPORTS = EXPORTS + RADIX_EXPORTS + ["fsc_client_keygen", "fsc_client_keygen_seeded", "fsc_client_set_encryption_seed", "fsc_client_free", "fsc_client_last_error", "fsc_client_server_keys",
                                      "fsc_client_secret_keys", "fsc_client_encrypt_blocks", "fsc_client_decrypt_blocks",
@@ -258,6 +259,12 @@ class Context:
         t = C.c_double()
         self._check(self.L.fsc_measure_fp64_peak(self.h, C.byref(t)))
         return t.value
+
+    def debug_fourier_key(self, stream_order=False):
+        """the Fourier bootstrapping key held by the context: [n][32][4][32] complex (test hook)"""
+        out = np.empty((self.params.lwe_dim, 32, 4, 32), dtype=np.complex128)
+        self._check(self.L.fsc_debug_fourier_key(self.h, _ptr(out), 1 if stream_order else 0))
+        return out
 
     def debug_negacyclic_mul(self, a, b):
         a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, self.params.poly_size)

@@ -63,6 +63,9 @@ void launch_pbs(int variant, int acc_bits, const void* bsk_fourier, const uint64
                 int sm_count, cudaStream_t st);
 void launch_negacyclic_mul(const uint64_t* a, const int64_t* b, uint64_t* c, int count, cudaStream_t st);
 
+// bsk_exact.cu: the same two layouts, correctly rounded (direct DFT in double-double arithmetic); either output may be null
+void launch_bsk_convert_exact(const uint64_t* bsk_std, void* out_ring, void* out_stream, int n, cudaStream_t st);
+
 // pbs_stream_kernel.cu (single-routine formulation; its own Fourier key layout)
 void launch_bsk_convert_stream(const uint64_t* bsk_std, void* bsk_fourier, int n, cudaStream_t st);
 void launch_pbs_stream(int acc_bits, const void* bsk_fourier, const uint64_t* in_small, int n, int base_log,
@@ -71,8 +74,12 @@ void launch_pbs_stream(int acc_bits, const void* bsk_fourier, const uint64_t* in
 // pbs_split_kernel.cu (latency form for narrow levels: four warps per ciphertext; the stream kernel's key layout)
 void launch_pbs_split(int acc_bits, const void* bsk_fourier, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
                       const uint32_t* lut_idx, const OutDest& out_big, const int32_t* out_idx, int count, cudaStream_t st);
+// pbs_solo_kernel.cu (wide batches, one warp per ciphertext, accumulator in tensor memory; the stream kernel's key layout; 32-bit accumulator)
+void launch_pbs_solo(const void* bsk_fourier, const uint64_t* in_small, int n, int base_log, const uint64_t* luts, const uint32_t* lut_idx,
+                     const OutDest& out_big, const int32_t* out_idx, int count, cudaStream_t st);
 void launch_negacyclic_mul_stream(const uint64_t* a, const int64_t* b, uint64_t* c, int count, cudaStream_t st);
-// 0: pair, 1: ring, 2: stream, 3: ring (wide) + stream (narrow) (FSC_PBS_VARIANT, else by accumulator width);
+// 0: pair, 1: ring, 2: stream, 3: ring (wide) + stream / split (narrow), 4: split, 5: solo (wide) + stream / split (narrow)
+// (FSC_PBS_VARIANT, else by accumulator width);
 // fixed per context at key upload
 int pbs_variant_for(int acc_bits);
 

@@ -238,7 +238,11 @@ __global__ void __launch_bounds__(64, 4) pbs_pair_kernel(const cplx* __restrict_
 //                s2tab [16][32] cplx (per-lane pass-2 constants) | full[NCH], empty[NCH] mbarriers
 // ---------------------------------------------------------------------------------------
 
-template <typename AccT, int CTS, int NCH, bool XH, bool HS, bool TX>
+// PP (TX only): FP64 turn-taking between the two warps of a ciphertext (same sub-partition): a warp waits for its turn
+// before each 32-point pass and hands the turn over after it (two named barriers per pair, ids 5..12).  Left alone the
+// two warps run every pass at the same time, each at half the pipe's rate, and then idle the pipe together during their
+// transposes / head / tail; taking turns pins them one pass apart, so one's transposes overlap the other's butterflies.
+template <typename AccT, int CTS, int NCH, bool XH, bool HS, bool TX, bool PP = false>
 __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                                      int n, int base_log, const uint64_t* __restrict__ luts,
                                                                      const uint32_t* __restrict__ lut_idx, const __grid_constant__ OutDest out_big,
@@ -361,6 +365,10 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
 
     // Fourier-domain product of this warp: X_p <- X_p * G[p][p] + X_{1-p} * G[1-p][p]  (g = 2 row + col)
     const int g_own = 3 * p, g_oth = 2 - p;
+    const int my_turn = 5 + 2 * ctl + p, other_turn = 5 + 2 * ctl + (1 - p);
+    auto turn_wait = [&]() { if constexpr (PP) asm volatile("bar.sync %0, 64;" ::"r"(my_turn) : "memory"); };
+    auto turn_pass = [&]() { if constexpr (PP) asm volatile("bar.arrive %0, 64;" ::"r"(other_turn) : "memory"); };
+    if (PP && p == 1) turn_pass();      // the p = 0 warp goes first
     int a_chunk = 0;
     int t = 0;                                          // ring chunk counter
     for (int i = 0; i < n; ++i) {
@@ -389,7 +397,9 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
         }
         if (HS) {      // forward passes in the 6-FMA tangent form (pass32), same node constants as dft32_fwd
             double* xb = reinterpret_cast<double*>(xbuf);
+            turn_wait();
             pass32(X, WT0Dev());
+            turn_pass();
             xpose_store_fwd_h(lane, xb, X, 0);
             __syncwarp();
             xpose_load_fwd_h(lane, xb, X, 0);
@@ -398,8 +408,10 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
             __syncwarp();
             xpose_load_fwd_h(lane, xb, X, 1);
             __syncwarp();
+            turn_wait();
             if constexpr (TX && FSC_TX_CONSTS) pass32(X, c2t);
             else pass32(X, c2s);
+            turn_pass();
         } else if (XH) warp_fft_fwd_h(lane, reinterpret_cast<double*>(xbuf), c2s, X);
         else warp_fft_fwd_c(lane, xbuf, c2s, X);
 
@@ -454,8 +466,10 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
             tmem_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(empty + st0); mbar_arrive(empty + st1); }
+            turn_wait();
             if constexpr (FSC_TX_CONSTS) pass32_inv_gs(X, c2t);
             else pass32_inv_gs(X, c2s);
+            turn_pass();
             {
                 double* xb = reinterpret_cast<double*>(xbuf);
                 xpose_store_inv_h(lane, xb, X, 0);
@@ -467,7 +481,9 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_ring_kernel(const cplx* __res
                 xpose_load_inv_h(lane, xb, X, 1);
                 __syncwarp();
             }
+            turn_wait();
             dft32_inv(X, S1PlainDev());
+            turn_pass();
             // tail: own-index pairs from tensor memory, updated values to shared memory (for the rotated reads) and back
             if constexpr (!FSC_TX_ACC) cmux_tail<AccT>(lane, acc, X);
             else
@@ -652,14 +668,14 @@ static void launch_pbs_pair_t(const void* bsk_f, const uint64_t* in_small, int n
                                                     lut_idx, out_big, out_idx, count);
 }
 
-template <typename AccT, int CTS, int NCH, bool XH, bool HS, bool TX = false>
+template <typename AccT, int CTS, int NCH, bool XH, bool HS, bool TX = false, bool PP = false>
 static void launch_pbs_ring_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
                               const uint32_t* lut_idx, const OutDest& out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     const size_t smem = (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>) + (size_t)CTS * 2 * (XH ? 512 : 1024) * sizeof(cplx) +
                         (size_t)NCH * (HS ? kHalfCplx : kChunkCplx) * sizeof(cplx) + 16 * 32 * sizeof(cplx) + 2 * NCH * sizeof(uint64_t) + 16;
-    ensure_dynamic_smem(reinterpret_cast<const void*>(&pbs_ring_kernel<AccT, CTS, NCH, XH, HS, TX>), smem);      // per device (the opt-in is a per-device attribute)
+    ensure_dynamic_smem(reinterpret_cast<const void*>(&pbs_ring_kernel<AccT, CTS, NCH, XH, HS, TX, PP>), smem);      // per device (the opt-in is a per-device attribute)
     const int grid = (count + CTS - 1) / CTS;
-    pbs_ring_kernel<AccT, CTS, NCH, XH, HS, TX><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log,
+    pbs_ring_kernel<AccT, CTS, NCH, XH, HS, TX, PP><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log,
                                                                         luts, lut_idx, out_big, out_idx, count);
 }
 
@@ -673,6 +689,7 @@ int pbs_variant_for(int acc_bits) {
     if (e && e[0] == 'p') return 0;
     if (e && e[0] == 'r') return 1;
     if (e && e[0] == 's' && e[1] == 'p') return 4;      // "split": the latency kernel at every width (tests)
+    if (e && e[0] == 's' && e[1] == 'o') return 5;      // "solo": one warp per ciphertext for wide batches, split / stream below
     if (e && e[0] == 's') return 2;
     if (e && e[0] == 'a') return 3;
     return acc_bits == 32 ? 3 : 1;
@@ -696,6 +713,7 @@ void launch_pbs(int variant, int acc_bits, const void* bsk_f, const uint64_t* in
         if (count <= sm_count) FSC_RING(uint32_t, 1, 3);
         else if (count <= 2 * sm_count) FSC_RING(uint32_t, 2, 3);
         else if (getenv("FSC_RING_NO_TMEM")) FSC_RING(uint32_t, 4, 2);      // partner exchange through shared memory (comparison)
+        else if (getenv("FSC_RING_PP")) launch_pbs_ring_t<uint32_t, 4, 2, true, true, true, true>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
         else launch_pbs_ring_t<uint32_t, 4, 2, true, true, true>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
     } else {
         // 64-bit accumulator: the chunked ring (8 KB chunks, blocking producer) measures faster than the half-step ring

@@ -258,6 +258,10 @@ const char *fsc_pbs_kernel_name(const fsc_ctx *ctx);
 /* Measures the device's sustained FP64 FMA rate (TFLOP/s, 2 flops per FMA) with a register-resident
  * FMA-chain kernel: the denominator of the blind rotation's compute roofline.                   */
 fsc_status fsc_measure_fp64_peak(fsc_ctx *ctx, double *tflops);
+/* Test hook: the Fourier-domain bootstrapping key as the context holds it (n * 32 * 4 * 32 complex doubles = 2 x that many
+ * doubles; stream_order = 0: ring-kernel layout [n][slot][g][lane], 1: stream-kernel layout [n][position][g][lane]).
+ * FSC_ERR_BAD_ARG if the context does not hold that layout.                                       */
+fsc_status fsc_debug_fourier_key(fsc_ctx *ctx, double *out, int32_t stream_order);
 /* c = a * b (negacyclic, mod 2^64) through the blind rotation's own FFT; a: count*N torus words,
  * b: count*N small signed integers (|b| < 2^23).  Host buffers.                                  */
 fsc_status fsc_debug_negacyclic_mul(fsc_ctx *ctx, const uint64_t *a, const int64_t *b, uint64_t *c, size_t count);

@@ -78,13 +78,15 @@ def test_pbs_all_messages_all_luts(gpu_ctx, oracle_keys, rng, preset, acc_bits):
 
 
 @pytest.mark.parametrize("acc_bits", [32, 64])
-@pytest.mark.parametrize("variant", ["auto", "stream", "ring", "pair", "split"])
+@pytest.mark.parametrize("variant", ["auto", "stream", "ring", "pair", "split", "solo"])
 def test_pbs_kernel_variants_all_widths(oracle_keys, orc, rng, variant, acc_bits, monkeypatch):
     """Every blind-rotation kernel (FSC_PBS_VARIANT) at batch widths that select each of its configurations
     (1, 2 and 3-4 ciphertexts per CTA, ragged last CTA): decrypted values equal the table, noise inside the budget.
     The Fourier key layout follows the variant, so this also checks both key conversions."""
     import fhe_sign_b200 as fsb
     from fhe_sign_b200.capi import LWE_BIG
+    if variant == "solo" and acc_bits != 32:
+        pytest.skip("the solo kernel exists for the 32-bit accumulator only")
     monkeypatch.setenv("FSC_PBS_VARIANT", variant)
     K = oracle_keys("toy")
     ctx = fsb.Context(fsb.Params.preset("toy", acc_bits=acc_bits))
@@ -280,3 +282,48 @@ def test_noise_gate_against_the_oracle_at_full_parameters(gpu_ctx, oracle_keys, 
     print("acc_bits=%d  sigma^2 GPU / CPU oracle = %.4f  (GPU 2^%.3f over %d, oracle 2^%.3f over %d)"
           % (acc_bits, var_gpu / var_cpu, 0.5 * np.log2(var_gpu), n_gpu, 0.5 * np.log2(var_cpu), n_cpu))
     assert var_gpu <= 1.05 * var_cpu, (var_gpu, var_cpu)
+
+
+def test_exact_fourier_key_is_correctly_rounded(oracle_keys, monkeypatch):
+    """bsk_exact.cu (direct DFT in double-double arithmetic, the default at key upload) against (a) the same transform in
+    80-bit long double on the host: equal to the last bit or two of a double, and (b) the kernels' own f64 FFT conversion
+    (FSC_BSK_CONVERT=fft): equal to FFT rounding (1e-16 relative rms) - in both key layouts."""
+    import fhe_sign_b200 as fsb
+    K = oracle_keys("toy")
+    n = K.params.lwe_dim
+
+    def keys(conv):
+        if conv:
+            monkeypatch.setenv("FSC_BSK_CONVERT", conv)
+        else:
+            monkeypatch.delenv("FSC_BSK_CONVERT", raising=False)
+        ctx = fsb.Context(fsb.Params.preset("toy", acc_bits=32))      # auto: ring layout + stream layout
+        ctx.upload_keys(K.bsk, K.ksk)
+        out = ctx.debug_fourier_key(False), ctx.debug_fourier_key(True)
+        ctx.close()
+        return out
+    ring_x, stream_x = keys(None)
+    ring_f, stream_f = keys("fft")
+    for x, f in ((ring_x, ring_f), (stream_x, stream_f)):
+        rel = np.sqrt((np.abs(x - f) ** 2).mean() / (np.abs(f) ** 2).mean())
+        assert 0 < rel < 1e-15, rel
+    # host reference in long double for a few polynomials: X_k = sum_j (a_j + i a_{j+1024}) zeta^(j (4k+1)), lane = k2, slot r: k1 = brev5(r)
+    brev5 = lambda v: ((v & 1) << 4) | ((v & 2) << 2) | (v & 4) | ((v & 8) >> 2) | ((v & 16) >> 4)
+    ld = np.longdouble
+    pi = ld("3.14159265358979323846264338327950288")
+    e = np.arange(4096).astype(ld)
+    cosv, sinv = np.cos(2 * pi * e / 4096), np.sin(2 * pi * e / 4096)
+    expo = np.outer(np.arange(1024), 4 * np.arange(1024) + 1) % 4096
+    Cm, Sm = cosv[expo], sinv[expo]
+    bsk = K.bsk.reshape(n, 4, 2048).view(np.int64)
+    worst = 0.0
+    for i, g in ((0, 0), (1, 3), (n - 1, 2)):
+        a = bsk[i, g]
+        zr, zi = a[:1024].astype(ld), a[1024:].astype(ld)
+        Xr, Xi = zr @ Cm - zi @ Sm, zr @ Sm + zi @ Cm
+        for r in range(32):
+            ks = np.arange(32) + 32 * brev5(r)
+            want = Xr[ks].astype(np.float64) + 1j * Xi[ks].astype(np.float64)
+            got = ring_x[i, r, g, :]
+            worst = max(worst, float(np.abs(got - want).max() / np.abs(want).max()))
+    assert worst < 4e-16, worst      # a couple of ulps (the host sum itself is only 64-bit accurate); the FFT conversion is ~50x that
