@@ -6,6 +6,26 @@
 
 #include "ctx.h"
 
+// NVTX ranges per radix operator (CUDA build only: the CPU mock / oracle builds of this file do not define FSC_NVTX), so that an
+// ncu / nsys capture of an operator is self-describing: "radix mul 128x128" > "level 16384" > kernels.
+#ifdef FSC_NVTX
+#include <nvtx3/nvToolsExt.h>
+#include <stdio.h>
+namespace {
+struct OpRange {
+    OpRange(const char* what, size_t a, size_t b) {
+        char name[96];
+        snprintf(name, sizeof(name), "radix %s %zu x %zu blocks", what, a, b);
+        nvtxRangePushA(name);
+    }
+    ~OpRange() { nvtxRangePop(); }
+};
+}  // namespace
+#define FSC_OP_RANGE(what, a, b) OpRange fsc_op_range__(what, a, b)
+#else
+#define FSC_OP_RANGE(what, a, b) do { } while (0)
+#endif
+
 using fsc::Block;
 using fsc::Radix;
 using fsc::RadixError;
@@ -100,6 +120,8 @@ fsc_status fsc_radix_len(const fsc_radix* a, size_t* n_blocks) {
 fsc_status fsc_radix_binary(fsc_ctx* ctx, uint32_t op, const fsc_radix* a, const fsc_radix* b, fsc_radix** out) {
     RX_BEGIN(ctx)
     need(a && b && out, "null argument");
+    static const char* const kNames[] = {"add", "sub", "mul", "min", "max", "shr", "shl", "and", "or", "xor", "lt", "eq"};
+    FSC_OP_RANGE(op < 12 ? kNames[op] : "?", a->blocks.size(), b->blocks.size());
     fsc::Evaluator& ev = *ctx->ev;
     Radix r;
     switch (op) {
@@ -124,6 +146,9 @@ fsc_status fsc_radix_binary(fsc_ctx* ctx, uint32_t op, const fsc_radix* a, const
 fsc_status fsc_radix_scalar(fsc_ctx* ctx, uint32_t op, const fsc_radix* a, const uint8_t* scalar_le, size_t n_bytes, fsc_radix** out) {
     RX_BEGIN(ctx)
     need(a && out && (scalar_le || !n_bytes), "null argument");
+    static const char* const kScalarNames[] = {"scalar add", "scalar sub", "scalar mul", "?", "?", "scalar shr", "scalar shl", "scalar and",
+                                               "?", "?", "?", "?", "scalar div", "scalar rem"};
+    FSC_OP_RANGE(op < 14 ? kScalarNames[op] : "?", a->blocks.size(), n_bytes * 4);
     fsc::Evaluator& ev = *ctx->ev;
     const size_t n = a->blocks.size();
     Radix r;
@@ -154,6 +179,7 @@ fsc_status fsc_radix_scalar(fsc_ctx* ctx, uint32_t op, const fsc_radix* a, const
 fsc_status fsc_radix_mul_wide(fsc_ctx* ctx, const fsc_radix* a, const fsc_radix* b, size_t out_blocks, fsc_radix** out) {
     RX_BEGIN(ctx)
     need(a && b && out, "null argument");
+    FSC_OP_RANGE("mul_wide", a->blocks.size(), b->blocks.size());
     emit(ctx, out, ctx->ev->mul(a->blocks, b->blocks, (int)out_blocks));
     RX_END(ctx)
 }
@@ -162,6 +188,7 @@ fsc_status fsc_radix_mul_add_wide(fsc_ctx* ctx, const fsc_radix* a, const fsc_ra
                                   fsc_radix** out) {
     RX_BEGIN(ctx)
     need(a && b && addend && out, "null argument");
+    FSC_OP_RANGE("mul_add_wide", a->blocks.size(), b->blocks.size());
     emit(ctx, out, ctx->ev->mul_add(a->blocks, b->blocks, &addend->blocks, (int)out_blocks));
     RX_END(ctx)
 }

@@ -2,6 +2,8 @@
 // A level (radix.h) = upload of a few index arrays, one lincomb launch producing the packed PBS
 // inputs, one keyswitch launch, one PBS launch scattering its outputs into the pool.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
+#include <stdio.h>
 #include <string.h>
 #include <unistd.h>
 
@@ -177,9 +179,18 @@ public:
     static int32_t lut_of(const LinReq&) { return 0; }
 
     // ---- levels ---------------------------------------------------------------------------------
+    struct LevelRange {      // NVTX: one range per PBS level, named by its width (and whether it is sharded)
+        LevelRange(size_t width, bool sharded) {
+            char name[64];
+            snprintf(name, sizeof(name), sharded ? "level %zu (sharded)" : "level %zu", width);
+            nvtxRangePushA(name);
+        }
+        ~LevelRange() { nvtxRangePop(); }
+    };
     void run_level(const std::vector<LevelReq>& reqs) override {
         if (reqs.empty()) return;
         eng->use();
+        LevelRange range(reqs.size(), exchange.active(reqs.size()));
         if (exchange.active(reqs.size())) {
             if (exchange.peer) run_level_peer(reqs); else run_level_sharded(reqs);
             return;
