@@ -13,7 +13,9 @@ namespace fsc {
 // symbolic block arithmetic
 // =======================================================================================
 bool noise_in_variance_units() {
-    static const bool v = [] { const char* e = getenv("FSC_RADIX_NOISE"); return e && e[0] == 'v'; }();
+    // default since round 2: variance units (measured on the GPU at sum c^2 = 25: tests/test_gpu_pbs.py::test_noise_budget_in_variance_units);
+    // FSC_RADIX_NOISE=linear restores the sum |c| <= 5 rule tfhe's NoiseLevel applies
+    static const bool v = [] { const char* e = getenv("FSC_RADIX_NOISE"); return !(e && e[0] == 'l'); }();
     return v;
 }
 

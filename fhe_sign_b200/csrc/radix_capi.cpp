@@ -120,8 +120,10 @@ fsc_status fsc_radix_len(const fsc_radix* a, size_t* n_blocks) {
 fsc_status fsc_radix_binary(fsc_ctx* ctx, uint32_t op, const fsc_radix* a, const fsc_radix* b, fsc_radix** out) {
     RX_BEGIN(ctx)
     need(a && b && out, "null argument");
+#ifdef FSC_NVTX
     static const char* const kNames[] = {"add", "sub", "mul", "min", "max", "shr", "shl", "and", "or", "xor", "lt", "eq"};
     FSC_OP_RANGE(op < 12 ? kNames[op] : "?", a->blocks.size(), b->blocks.size());
+#endif
     fsc::Evaluator& ev = *ctx->ev;
     Radix r;
     switch (op) {
@@ -146,9 +148,11 @@ fsc_status fsc_radix_binary(fsc_ctx* ctx, uint32_t op, const fsc_radix* a, const
 fsc_status fsc_radix_scalar(fsc_ctx* ctx, uint32_t op, const fsc_radix* a, const uint8_t* scalar_le, size_t n_bytes, fsc_radix** out) {
     RX_BEGIN(ctx)
     need(a && out && (scalar_le || !n_bytes), "null argument");
+#ifdef FSC_NVTX
     static const char* const kScalarNames[] = {"scalar add", "scalar sub", "scalar mul", "?", "?", "scalar shr", "scalar shl", "scalar and",
                                                "?", "?", "?", "?", "scalar div", "scalar rem"};
     FSC_OP_RANGE(op < 14 ? kScalarNames[op] : "?", a->blocks.size(), n_bytes * 4);
+#endif
     fsc::Evaluator& ev = *ctx->ev;
     const size_t n = a->blocks.size();
     Radix r;

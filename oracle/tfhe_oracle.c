@@ -148,6 +148,7 @@ static void r4_fwd(const fft_plan *pl, double *re, double *im, uint32_t len) {
                      *w3r = pl->w3r + q - 1, *w3i = pl->w3i + q - 1;
         for (uint32_t s = 0; s < len; s += 4 * q) {
             double *ar = re + s, *ai = im + s, *br = ar + q, *bi = ai + q, *cr = br + q, *ci = bi + q, *dr = cr + q, *di = ci + q;
+#pragma omp simd
             for (uint32_t j = 0; j < q; j++) {
                 const double t0r = ar[j] + cr[j], t0i = ai[j] + ci[j], t1r = ar[j] - cr[j], t1i = ai[j] - ci[j];
                 const double t2r = br[j] + dr[j], t2i = bi[j] + di[j];
@@ -169,6 +170,7 @@ static void r4_inv(const fft_plan *pl, double *re, double *im, uint32_t len) {
                      *w3r = pl->w3r + q - 1, *w3i = pl->w3i + q - 1;
         for (uint32_t s = 0; s < len; s += 4 * q) {
             double *ar = re + s, *ai = im + s, *br = ar + q, *bi = ai + q, *cr = br + q, *ci = bi + q, *dr = cr + q, *di = ci + q;
+#pragma omp simd
             for (uint32_t j = 0; j < q; j++) {
                 const double y0r = ar[j], y0i = ai[j];
                 const double y1r = br[j] * w1r[j] + bi[j] * w1i[j], y1i = bi[j] * w1r[j] - br[j] * w1i[j];   /* times conj(w^j) */
@@ -189,6 +191,7 @@ static void r4_inv(const fft_plan *pl, double *re, double *im, uint32_t len) {
 /* in: real coefficients as doubles c[0..N); out: re/im [M] (scrambled order) */
 static void fft_fwd(const fft_plan *pl, const double *c, double *re, double *im) {
     const uint32_t M = pl->M;
+#pragma omp simd
     for (uint32_t j = 0; j < M; j++) {
         double a = c[j], b = c[j + M];
         re[j] = a * pl->twr[j] - b * pl->twi[j];
@@ -196,6 +199,7 @@ static void fft_fwd(const fft_plan *pl, const double *c, double *re, double *im)
     }
     if (pl->has_radix2) {
         const uint32_t h = M / 2;
+#pragma omp simd
         for (uint32_t j = 0; j < h; j++) {
             double ur = re[j], ui = im[j], vr = re[j + h], vi = im[j + h];
             double dr = ur - vr, di = ui - vi;
@@ -215,6 +219,7 @@ static void fft_inv(const fft_plan *pl, double *re, double *im, double *c) {
     if (pl->has_radix2) {
         const uint32_t h = M / 2;
         r4_inv(pl, re, im, h); r4_inv(pl, re + h, im + h, h);
+#pragma omp simd
         for (uint32_t j = 0; j < h; j++) {
             double vr = re[j + h] * pl->r2r[j] + im[j + h] * pl->r2i[j];
             double vi = im[j + h] * pl->r2r[j] - re[j + h] * pl->r2i[j];
@@ -226,6 +231,7 @@ static void fft_inv(const fft_plan *pl, double *re, double *im, double *c) {
         r4_inv(pl, re, im, M);
     }
     const double sc = 1.0 / (double)M;
+#pragma omp simd
     for (uint32_t j = 0; j < M; j++) {
         double a = re[j] * sc, b = im[j] * sc;
         c[j]     = a * pl->twr[j] + b * pl->twi[j];    /* times conj(twist) */
@@ -507,6 +513,7 @@ static void external_product_add(const orc_keys *K, uint32_t i, pbs_scratch *s) 
                 const size_t off = ((((size_t)i * k1 + pp) * L + l) * k1 + q) * M;
                 const double *gr = K->bsk_re + off, *gi = K->bsk_im + off;
                 double *orr = s->ore + (size_t)q * M, *oii = s->oim + (size_t)q * M;
+#pragma omp simd
                 for (uint32_t t = 0; t < M; t++) {
                     orr[t] += s->fre[t] * gr[t] - s->fim[t] * gi[t];
                     oii[t] += s->fre[t] * gi[t] + s->fim[t] * gr[t];

@@ -327,3 +327,45 @@ def test_exact_fourier_key_is_correctly_rounded(oracle_keys, monkeypatch):
             got = ring_x[i, r, g, :]
             worst = max(worst, float(np.abs(got - want).max() / np.abs(want).max()))
     assert worst < 4e-16, worst      # a couple of ulps (the host sum itself is only 64-bit accurate); the FFT conversion is ~50x that
+
+
+@pytest.mark.parametrize("combo", ["7 unit terms", "4x + 3y"])
+def test_noise_budget_in_variance_units(gpu_ctx, oracle_keys, combo):
+    """Evidence for FSC_RADIX_NOISE=variance (radix.h): the parameter set's budget is a VARIANCE, nu^2 = 25 fresh-PBS
+    variances at the input of a lookup, so a linear combination of independent fresh blocks is admissible when
+    sum c^2 <= 25 - 7 unit terms (sum |c| = 7 would be refused by the linear rule) or 4x + 3y (sum c^2 = 25 exactly).
+    Measured on real ciphertexts at the full 2_2 parameters: 102 400 such combinations of fresh GPU bootstraps go through
+    one more lookup with zero decode failures, and the noise that lookup sees (combination + keyswitch, measured under the
+    small key on a sample; + the analytic modulus-switch term) leaves z = radius / sigma >= 9.2 (p_fail <= 2^-64: what the
+    parameter set is designed for - keyswitch and modulus switch are 99 % of that noise, the combination under 1 %)."""
+    import math
+    K, ctx = oracle_keys("2_2_gaussian"), gpu_ctx("2_2_gaussian", 32)
+    ident = ctx.luts_from_tables(np.arange(16))
+    rng = np.random.default_rng(31)
+    coefs, tops = ([1] * 7, [2] * 7) if combo.startswith("7") else ([4, 3], [3, 1])      # value <= 14 / 15: inside the 4-bit space
+    total, chunk, fails, sq_big = 102400, 12800, 0, 0.0
+    small_err = []
+    for s in range(total // chunk):
+        acc = np.zeros((chunk, 2049), dtype=np.uint64)
+        want = np.zeros(chunk, dtype=np.uint64)
+        for t, (c, top) in enumerate(zip(coefs, tops)):
+            m = rng.integers(0, top + 1, chunk).astype(np.uint64)
+            fresh = ctx.apply_lut_host(K.encrypt_msgs(m, seed=40 + t, stream=s * chunk), ident)      # a fresh bootstrap output
+            with np.errstate(over="ignore"):
+                acc += fresh * np.uint64(c)
+            want += m * np.uint64(c)
+        out = ctx.apply_lut_host(acc, ident)
+        fails += int((K.decrypt_msgs(out) != want).sum())
+        e = _noise(K, acc, want)
+        sq_big += float((e * e).sum())
+        if s == 0:      # noise under the small key after the keyswitch, on 2 048 of them (CPU keyswitch = the GPU's, bit for bit)
+            ks = K.keyswitch(acc[:2048])
+            small_err = (K.phase_small(ks) - K.encode(want[:2048])).astype(np.int64).astype(np.float64) / 2.0**64
+    n = K.params.lwe_dim
+    var_in = float((small_err ** 2).mean())
+    var_ms = (n / 2 + 1) / (12.0 * 4096.0**2)              # rounding of n/2 + 1 mask terms (binary key) to multiples of 1/4096
+    z = 2.0**-6 / math.sqrt(var_in + var_ms)               # decoding radius: half a plaintext step, Delta / 2 = 2^-6 of the torus
+    print("%s: sigma combination 2^%.2f (sum c^2 = %d), sigma after keyswitch 2^%.2f, + modulus switch 2^%.2f -> z = %.1f, %d failures in %d"
+          % (combo, 0.5 * math.log2(sq_big / total), sum(c * c for c in coefs), 0.5 * math.log2(var_in), 0.5 * math.log2(var_in + var_ms), z, fails, total))
+    assert fails == 0
+    assert z >= 9.2

@@ -273,7 +273,7 @@ def test_rem_by_pseudo_mersenne_moduli_folds(M):
 
 
 def test_variance_unit_noise_bookkeeping_is_a_relaxation():
-    """FSC_RADIX_NOISE=variance (experimental, off by default): same decrypted results, fewer bootstraps in a wide product
+    """FSC_RADIX_NOISE=variance (the default since the GPU noise measurement of round 2) against =linear: same decrypted results, fewer bootstraps in a wide product
     (column-sum chunks may hold more low-degree terms).  The switch is read once per process, hence the subprocess."""
     import os
     import subprocess
