@@ -312,11 +312,11 @@ def run_ops(fsb, local, rank, world, dist, torch):
     golden = json.load(open(os.path.join(ROOT, "tests", "golden", "schnorr_vectors.json")))
     bg.set_server_key(ctx)
 
-    def sign_row(v):
+    def sign_row(v, public_challenge=False):
         d, k0, msg = int(v["secret_key"], 16), int(v["k0"], 16), bytes.fromhex(v["message"])
         p0, _ = R.stats()
         t0 = time.perf_counter()
-        sig = schnorr.sign_fhe_with_k0(msg, k0, d, BigUintFHE.new(d, ck), ck, fused=True)
+        sig = schnorr.sign_fhe_with_k0(msg, k0, d, BigUintFHE.new(d, ck), ck, fused=True, public_challenge=public_challenge)
         dt = time.perf_counter() - t0
         p1, _ = R.stats()
         return dt, p1 - p0, sig.to_bytes().hex().upper() == v["reference_signature"]
@@ -330,6 +330,15 @@ def run_ops(fsb, local, rank, world, dist, torch):
     sign["one_signature_pbs"] = pbs
     sign["one_signature_gpus"] = world
     all_ok = ok1
+    # (1b) protocol-level variant, reported separately (NOT the reference's dataflow, which encrypts e too): the challenge e is
+    # public by construction, so k + e*d can be a scalar x ciphertext product; d and k stay encrypted, same signature bytes
+    sign_row(golden[1], public_challenge=True)
+    sync_all()
+    dt, pbs, okp = sign_row(golden[1], public_challenge=True)
+    sign["public_challenge_variant"] = {"one_signature_s": round(tmax(dt), 4), "pbs": pbs, "match": bool(okp),
+                                        "note": "e = H(R || P || m) in plaintext (every verifier recomputes it), d and k encrypted: "
+                                                "fsc_radix_scalar_mul_add_wide; not the reference's dataflow"}
+    all_ok = all_ok and okp
     # (2) all 8 rows: world == 1 sequentially; world > 1 as independent signatures, row r on rank r mod world, no exchange
     if world > 1:
         from fhe_sign_b200.distributed import disable_peer_sharding

@@ -172,6 +172,19 @@ class BigUintFHE:
         total = api.mul_add_wide(e._as_radix(), d._as_radix(), k._as_radix(), BLOCKS_U32 * n_out)
         return BigUintFHE._from_radix(total, n_out, k.client_key)
 
+    @staticmethod
+    def scalar_mul_add_fused(k, e_plain, d):
+        """k + e*d with the challenge e in PLAINTEXT (public by construction: every verifier recomputes it), d and k encrypted:
+        fsc_radix_scalar_mul_add_wide.  Same digit-count conventions as mul_add_fused."""
+        api = _api()
+        e_plain = int(e_plain)
+        if e_plain == 0 or not d.digits:
+            return k + BigUintFHE([], k.client_key)
+        n_prod = (e_plain.bit_length() + 31) // 32 + len(d.digits)
+        n_out = max(len(k.digits), n_prod) + 1
+        total = api.scalar_mul_add_wide(d._as_radix(), e_plain, k._as_radix(), BLOCKS_U32 * n_out)
+        return BigUintFHE._from_radix(total, n_out, k.client_key)
+
     def rem_scalar(self, modulus):
         """self mod a plaintext modulus, homomorphically (the reference takes `% n` after decryption,
         src/schnorr.rs:276).  Digits follow the modulus' width."""

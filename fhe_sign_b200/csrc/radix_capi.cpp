@@ -197,6 +197,15 @@ fsc_status fsc_radix_mul_add_wide(fsc_ctx* ctx, const fsc_radix* a, const fsc_ra
     RX_END(ctx)
 }
 
+fsc_status fsc_radix_scalar_mul_add_wide(fsc_ctx* ctx, const fsc_radix* a, const uint8_t* scalar_le, size_t n_bytes, const fsc_radix* addend,
+                                         size_t out_blocks, fsc_radix** out) {
+    RX_BEGIN(ctx)
+    need(a && out && (scalar_le || !n_bytes), "null argument");
+    FSC_OP_RANGE("scalar_mul_add_wide", a->blocks.size(), n_bytes * 4);
+    emit(ctx, out, ctx->ev->scalar_mul_add(a->blocks, scalar_digits(scalar_le, n_bytes, 0), addend ? &addend->blocks : nullptr, (int)out_blocks));
+    RX_END(ctx)
+}
+
 fsc_status fsc_radix_cast(fsc_ctx* ctx, const fsc_radix* a, size_t n_blocks, fsc_radix** out) {
     RX_BEGIN(ctx)
     need(a && out, "null argument");

@@ -10,7 +10,7 @@ OPS = dict(add=0, sub=1, mul=2, min=3, max=4, shr=5, shl=6, and_=7, or_=8, xor=9
 WORDS = 2049
 
 RADIX_EXPORTS = ["fsc_radix_from_lwe", "fsc_radix_to_lwe", "fsc_radix_trivial", "fsc_radix_clone", "fsc_radix_free",
-                 "fsc_radix_len", "fsc_radix_binary", "fsc_radix_scalar", "fsc_radix_mul_wide", "fsc_radix_mul_add_wide", "fsc_radix_cast",
+                 "fsc_radix_len", "fsc_radix_binary", "fsc_radix_scalar", "fsc_radix_mul_wide", "fsc_radix_mul_add_wide", "fsc_radix_scalar_mul_add_wide", "fsc_radix_cast",
                  "fsc_radix_slice", "fsc_radix_concat", "fsc_radix_sum", "fsc_radix_select", "fsc_radix_stats",
                  "fsc_radix_stats2", "fsc_set_level_exchange", "fsc_peer_pool_export", "fsc_peer_pool_connect",
                  "fsc_peer_pool_disconnect"]
@@ -25,6 +25,7 @@ def declare(L):
         "fsc_radix_len": [vp, C.POINTER(sz)], "fsc_radix_binary": [vp, u32, vp, vp, pp],
         "fsc_radix_scalar": [vp, u32, vp, vp, sz, pp], "fsc_radix_mul_wide": [vp, vp, vp, sz, pp],
         "fsc_radix_mul_add_wide": [vp, vp, vp, vp, sz, pp],
+        "fsc_radix_scalar_mul_add_wide": [vp, vp, vp, sz, vp, sz, pp],
         "fsc_radix_cast": [vp, vp, sz, pp], "fsc_radix_slice": [vp, vp, sz, sz, pp],
         "fsc_radix_concat": [vp, vp, sz, pp], "fsc_radix_sum": [vp, vp, sz, sz, pp],
         "fsc_radix_select": [vp, vp, vp, vp, pp], "fsc_radix_stats": [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
@@ -114,6 +115,11 @@ class RadixApi:
     def mul_add_wide(self, a, b, addend, out_blocks):
         """a * b + addend with one carry propagation (the addend joins the product's column sum)."""
         return self._new(self.L.fsc_radix_mul_add_wide, a.h, b.h, addend.h, out_blocks)
+
+    def scalar_mul_add_wide(self, a, scalar, addend, out_blocks):
+        """a * scalar + addend (scalar in plaintext), one carry propagation."""
+        buf, n = int_to_le(scalar)
+        return self._new(self.L.fsc_radix_scalar_mul_add_wide, a.h, buf, n, addend.h if addend is not None else None, out_blocks)
 
     def cast(self, a, n_blocks):
         return self._new(self.L.fsc_radix_cast, a.h, n_blocks)

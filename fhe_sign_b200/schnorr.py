@@ -64,17 +64,25 @@ class Signature:
         return _b32(self.r_x) + _b32(self.s)
 
 
-def sign_fhe_with_k0(message, k0, privkey, privkey_fhe, client_key, fused=False, reduce_encrypted=False):
+def sign_fhe_with_k0(message, k0, privkey, privkey_fhe, client_key, fused=False, reduce_encrypted=False, public_challenge=False):
     """src/schnorr.rs:235-290.  `privkey` is the plaintext key (used only for the public key, :241);
     `privkey_fhe` is its BigUintFHE encryption.  fused=True evaluates the same expression with the
     batched schedule (BigUintFHE.mul_add_fused).  reduce_encrypted=True also takes `mod n` under encryption
-    (SURVEY.md 8f.2), so that only the 256-bit s is ever decrypted; the reference reduces in plaintext (:276)."""
+    (SURVEY.md 8f.2), so that only the 256-bit s is ever decrypted; the reference reduces in plaintext (:276).
+    public_challenge=True is a protocol-level variant, NOT the reference's dataflow: the challenge e = H(R || P || m) is public by
+    construction (verify recomputes it, :307-345), so it is handed to the server in plaintext and k + e*d becomes a
+    scalar-times-ciphertext product (fsc_radix_scalar_mul_add_wide); d and the nonce k stay encrypted.  Same signature bytes."""
     pubkey = get_public_key_with_even_y(privkey)
     r = _mul(k0)
     k = N - k0 if r[1] % 2 == 1 else k0
     e = compute_challenge(r, pubkey, message)
-    e_fhe = BigUintFHE.new(e, client_key)
     k_fhe = BigUintFHE.new(k, client_key)
+    if public_challenge:
+        s_fhe = BigUintFHE.scalar_mul_add_fused(k_fhe, e, privkey_fhe.clone())
+        if reduce_encrypted:
+            s_fhe = s_fhe.rem_scalar(N)
+        return Signature(r[0], s_fhe.to_biguint(client_key) % N)
+    e_fhe = BigUintFHE.new(e, client_key)
     if fused:
         s_fhe = BigUintFHE.mul_add_fused(k_fhe, e_fhe, privkey_fhe.clone())
     else:

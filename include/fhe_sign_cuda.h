@@ -159,6 +159,12 @@ fsc_status fsc_radix_mul_wide(fsc_ctx *ctx, const fsc_radix *a, const fsc_radix 
  * both - the fused form of `k_fhe + (e_fhe * privkey_fhe)` (src/schnorr.rs:274).                  */
 fsc_status fsc_radix_mul_add_wide(fsc_ctx *ctx, const fsc_radix *a, const fsc_radix *b, const fsc_radix *addend,
                                   size_t out_blocks, fsc_radix **out);
+/* a * scalar + addend, out_blocks result blocks, scalar = little-endian bytes: the product's digit multiples cost two lookups per
+ * block and the addend rides in the column sum.  Use: k + e*d with the challenge e taken in PLAINTEXT - e is public by
+ * construction (every verifier recomputes it from R, P and the message: src/schnorr.rs:267, :307-345), only d and k need to stay
+ * encrypted.  This is not the reference's dataflow (it encrypts e too, src/schnorr.rs:272); 3.5x fewer bootstraps.          */
+fsc_status fsc_radix_scalar_mul_add_wide(fsc_ctx *ctx, const fsc_radix *a, const uint8_t *scalar_le, size_t n_bytes,
+                                         const fsc_radix *addend, size_t out_blocks, fsc_radix **out);
 /* FheUintM::cast_from (src/biguint.rs:110,116,135-137): truncate or zero-extend; no device work.  */
 fsc_status fsc_radix_cast(fsc_ctx *ctx, const fsc_radix *a, size_t n_blocks, fsc_radix **out);
 fsc_status fsc_radix_slice(fsc_ctx *ctx, const fsc_radix *a, size_t first, size_t n_blocks, fsc_radix **out);

@@ -101,6 +101,21 @@ def test_sign_fhe_with_k0_all_vectors(ck, fused):
         assert sig.to_bytes() == sm.sign_with_k0(msg, k0, d)
 
 
+def test_sign_with_the_public_challenge_variant(ck):
+    """k + e*d with the challenge e handed over in plaintext (it is public: verify recomputes it) and d, k encrypted:
+    fsc_radix_scalar_mul_add_wide.  Same signature bytes as the reference's plaintext twin on every signing row, and about a third
+    of the bootstraps of the ciphertext x ciphertext schedule."""
+    api = bg._api()
+    for v in GOLDEN:
+        d, k0, msg = int(v["secret_key"], 16), int(v["k0"], 16), bytes.fromhex(v["message"])
+        p0, _ = api.stats()
+        sig = schnorr.sign_fhe_with_k0(msg, k0, d, BigUintFHE.new(d, ck), ck, public_challenge=True)
+        p1, _ = api.stats()
+        assert sig.to_bytes().hex().upper() == v["reference_signature"]
+        if v["index"] == 1:
+            assert p1 - p0 < 20000, p1 - p0
+
+
 def test_sign_with_the_reduction_under_encryption(ck):
     """`s = (k + e d) mod n` entirely under encryption (folding reduction by the secp256k1 order), then the
     same signature bytes as the reference's plaintext `% n` (src/schnorr.rs:276)."""

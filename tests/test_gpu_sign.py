@@ -89,6 +89,20 @@ def test_sign_fhe_with_k0_all_vectors_fused(ck):
             assert sig.to_bytes().hex().upper() == v["csv_signature"].upper()
 
 
+def test_sign_with_public_challenge_on_gpu(ck):
+    """the scalar-challenge variant (e in plaintext, d and k encrypted: fsc_radix_scalar_mul_add_wide) on real ciphertexts:
+    the reference's signature bytes for every signing row."""
+    for v in GOLDEN:
+        d, k0, msg = int(v["secret_key"], 16), int(v["k0"], 16), bytes.fromhex(v["message"])
+        p0, l0 = bg._api().stats()
+        t0 = time.perf_counter()
+        sig = schnorr.sign_fhe_with_k0(msg, k0, d, BigUintFHE.new(d, ck), ck, public_challenge=True)
+        dt = time.perf_counter() - t0
+        p1, l1 = bg._api().stats()
+        print("public-challenge sign, vector %d: %.2f s, %d PBS in %d levels" % (v["index"], dt, p1 - p0, l1 - l0))
+        assert sig.to_bytes().hex().upper() == v["reference_signature"]
+
+
 def test_product_only_pipeline_no_oracle():
     """keys, encryption, GPU evaluation and decryption all through the product's own C ABI (fsc_client_* +
     fsc_radix_*): the oracle is not involved.  Known answers of src/biguint.rs:407-426 and vector 1 signing."""
