@@ -248,21 +248,36 @@ def run_ops(fsb, local, rank, world, dist, torch):
     # test-style reproducible keys AND encryption randomness: every rank must hold identical ciphertexts (SPMD contract)
     ck, (bsk, ksk) = generate_keys(PRESET, seed=2024, encryption_seed=7)
     t_keygen = time.perf_counter() - t0
-    ctx = fsb.Context(fsb.Params.preset(PRESET, acc_bits=ACC_BITS), device=local)
+    stream = torch.cuda.Stream() if world > 1 else None      # the NCCL-callback fallback enqueues its all-gather on the context's stream
+    ctx = fsb.Context(fsb.Params.preset(PRESET, acc_bits=ACC_BITS), device=local, stream=stream.cuda_stream if stream else 0)
     t0 = time.perf_counter()
     ctx.upload_keys(bsk, ksk)
     t_upload = time.perf_counter() - t0
     R = ctx.radix
     exchange = "none (1 GPU)"
+    peer_on = False
     if world > 1:
+        from fhe_sign_b200.distributed import enable_level_sharding, enable_peer_sharding
         mode = os.environ.get("FSC_BENCH_EXCHANGE", "peer")
         min_width = int(os.environ.get("FSC_SHARD_MIN", "149"))
+        ok = 0.0
         if mode == "peer":
-            from fhe_sign_b200.distributed import enable_peer_sharding
-            enable_peer_sharding(ctx, min_width=min_width)
+            try:
+                enable_peer_sharding(ctx, min_width=min_width)
+                ok = 1.0
+            except Exception as e:      # no peer access / IPC on this box: every rank must take the same path
+                print("peer-mapped exchange unavailable on rank %d: %r" % (rank, e), file=sys.stderr)
+        t = torch.tensor([ok], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if float(t[0]) == 1.0:
+            peer_on = True
             exchange = "peer-mapped block pools: blind-rotation epilogue stores into every rank's pool over NVLink + flag barrier kernel (fsc_peer_pool_*)"
         else:
-            raise SystemExit("FSC_BENCH_EXCHANGE=%s: only the library-owned peer exchange is wired into bench.py (tools/multi_gpu_ops.py compares it with the NCCL callback form)" % mode)
+            if ok:
+                from fhe_sign_b200.distributed import disable_peer_sharding
+                disable_peer_sharding(ctx)
+            enable_level_sharding(ctx, stream, min_width=min_width, capacity_blocks=1 << 16)
+            exchange = "NCCL all-gather per level through the fsc_set_level_exchange callback (peer-mapped pools unavailable or FSC_BENCH_EXCHANGE=nccl)"
 
     def sync_all():
         ctx.sync()
@@ -341,8 +356,13 @@ def run_ops(fsb, local, rank, world, dist, torch):
     all_ok = all_ok and okp
     # (2) all 8 rows: world == 1 sequentially; world > 1 as independent signatures, row r on rank r mod world, no exchange
     if world > 1:
-        from fhe_sign_b200.distributed import disable_peer_sharding
-        disable_peer_sharding(ctx)
+        if peer_on:
+            from fhe_sign_b200.distributed import disable_peer_sharding
+            disable_peer_sharding(ctx)
+        else:
+            ctx.sync()
+            dist.barrier()
+            ctx._check(ctx.L.fsc_set_level_exchange(ctx.h, 0, 1, 0, None, 0, None, None))      # world = 1: sharding off
     sync_all()
     t0 = time.perf_counter()
     rows = []
