@@ -341,6 +341,9 @@ public:
         for (void* o : peer_opened) cudaIpcCloseMemHandle(o);
         peer_opened.clear();
         exchange = Exchange();
+        // the pool may grow again - the caller guarantees that every rank has disconnected before any of them allocates
+        // (fhe_sign_b200/distributed.py: a host barrier on both sides of the call)
+        peer_fixed = false;
     }
 
     void run_linear(const std::vector<LinReq>& reqs) override {

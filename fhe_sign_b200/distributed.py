@@ -106,3 +106,4 @@ def disable_peer_sharding(ctx, group=None):
     ctx.sync()
     dist.barrier(group=group)      # every rank is done writing into every pool
     ctx._check(ctx.L.fsc_peer_pool_disconnect(ctx.h))
+    dist.barrier(group=group)      # every rank has unmapped every pool: they may be reallocated from here on

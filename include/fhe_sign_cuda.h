@@ -198,6 +198,8 @@ fsc_status fsc_set_level_exchange(fsc_ctx *ctx, int32_t rank, int32_t world, siz
 #define FSC_PEER_HANDLE_BYTES 128
 fsc_status fsc_peer_pool_export(fsc_ctx *ctx, size_t capacity_blocks, uint8_t *handle_out);
 fsc_status fsc_peer_pool_connect(fsc_ctx *ctx, int32_t rank, int32_t world, size_t min_width, const uint8_t *handles);
+/* Unmaps the peers' pools and turns sharding off.  All ranks call it together: a host-side barrier before (nobody still writes
+ * into a pool) and after (nobody still maps a pool that is about to be reallocated).                                   */
 fsc_status fsc_peer_pool_disconnect(fsc_ctx *ctx);
 /* bootstraps, PBS levels and sharded levels issued by the radix layer so far on this context     */
 fsc_status fsc_radix_stats2(const fsc_ctx *ctx, uint64_t *pbs_count, uint64_t *level_count, uint64_t *sharded_levels);
