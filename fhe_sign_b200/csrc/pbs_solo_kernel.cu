@@ -132,6 +132,11 @@ __global__ void __launch_bounds__(kSoloCts * 32, 1) pbs_solo_kernel(const cplx* 
         if ((i & 31) == 0) a_chunk = (i + lane < n) ? modswitch(ct[i + lane]) : 0;
         const int a = __shfl_sync(0xffffffffu, a_chunk, i & 31);
         if (trace && blockIdx.x == 0 && lane == 0 && (i & 63) == 0) trace[(i >> 6) * kSoloCts + warp] = clock64();      // diagnostic (FSC_SOLO_TRACE)
+        // diagnostic: phase boundaries of warps 0 and 4 at step 512 (32 stamps each, behind the per-step rows)
+        long long* stamps = (trace && blockIdx.x == 0 && lane == 0 && i == 512 && (warp & 3) == 0) ? trace + (n / 64 + 1) * kSoloCts + (warp >> 2) * 32 : nullptr;
+        int n_stamp = 0;
+#define FSC_STAMP() do { if (stamps) stamps[n_stamp++] = clock64(); } while (0)
+        FSC_STAMP();
 
         // rotation constants of this step (pbs_head.cuh stream_head_u32)
         const int base = (lane - a) & 4095;
@@ -190,6 +195,7 @@ __global__ void __launch_bounds__(kSoloCts * 32, 1) pbs_solo_kernel(const cplx* 
                     }
                 }
                 __syncwarp();      // the scratch is the transpose buffer of the passes below
+                FSC_STAMP();       // head done
             } else if (t == 3) {
                 // ---- output 0 of the product comes back from tensor memory (position order -> slot)
 #pragma unroll
@@ -199,14 +205,17 @@ __global__ void __launch_bounds__(kSoloCts * 32, 1) pbs_solo_kernel(const cplx* 
 #pragma unroll
                     for (int rr = 0; rr < 4; ++rr) X[freq_at(4 * k + rr)] = o4[rr];
                 }
+                FSC_STAMP();       // spectrum reload done
             }
 
             // ---- two passes of the one routine with a transpose between them (forward: tables 0, 1; inverse: 2, 3)
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
                 if (PP) turn_wait(my_turn);
+                FSC_STAMP();       // turn taken
                 pass32(X, pass_table(tabs, (t < 2 ? 0 : 2) + h, lane));
                 if (PP) turn_pass(other_turn);
+                FSC_STAMP();       // pass done
                 if (h == 0) {
                     const int row = t < 2 ? lane : row_inv;
                     xp_store(lane, xb, X, 0);
@@ -217,6 +226,7 @@ __global__ void __launch_bounds__(kSoloCts * 32, 1) pbs_solo_kernel(const cplx* 
                     __syncwarp();
                     xp_load(row, xb, X, 1);
                     __syncwarp();
+                    FSC_STAMP();   // transpose done
                 }
             }
 
@@ -230,6 +240,7 @@ __global__ void __launch_bounds__(kSoloCts * 32, 1) pbs_solo_kernel(const cplx* 
                     tmem_st4(t_spec + 16 * k, v4);
                 }
                 tmem_wait_st();
+                FSC_STAMP();       // spectrum parked
             } else if (t == 1) {
                 // ---- Fourier-domain product: Y_q = X_0 G[0][q] + X_1 G[1][q]; Y_1 -> registers, Y_0 -> tensor memory
                 if (producer) {      // both halves of this step requested before this warp sleeps on them
@@ -274,6 +285,7 @@ __global__ void __launch_bounds__(kSoloCts * 32, 1) pbs_solo_kernel(const cplx* 
                 tmem_wait_st();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(empty + st0); mbar_arrive(empty + st1); }
+                FSC_STAMP();       // product done
             } else {
                 // ---- tail: twist, rounding, accumulation into the own-index pairs in tensor memory
                 const cplx* tw = tabs + kTabTwist + lane;
@@ -300,8 +312,10 @@ __global__ void __launch_bounds__(kSoloCts * 32, 1) pbs_solo_kernel(const cplx* 
                 }
                 if (PP == 2) turn_pass(other_turn);
                 tmem_wait_st();
+                FSC_STAMP();       // tail done
             }
         }
+#undef FSC_STAMP
     }
 
     // ---- sample extraction of coefficient 0: the mask polynomial through the scratch, the body's coefficient 0 from lane 0
@@ -342,14 +356,15 @@ static void launch_pbs_solo_t(const void* bsk_f, const uint64_t* in_small, int n
     static const bool want_trace = getenv("FSC_SOLO_TRACE") != nullptr;      // diagnostic: per-warp clock at every 64th step of CTA 0
     long long* trace = nullptr;
     const int rows = n / 64 + 1;
+    const size_t trace_words = (size_t)rows * kSoloCts + 64;      // + 2 x 32 phase stamps
     if (want_trace) {
-        FSC_CUDA_CHECK(cudaMalloc(&trace, (size_t)rows * kSoloCts * sizeof(long long)));
-        FSC_CUDA_CHECK(cudaMemsetAsync(trace, 0, (size_t)rows * kSoloCts * sizeof(long long), st));
+        FSC_CUDA_CHECK(cudaMalloc(&trace, trace_words * sizeof(long long)));
+        FSC_CUDA_CHECK(cudaMemsetAsync(trace, 0, trace_words * sizeof(long long), st));
     }
     pbs_solo_kernel<NH, PP><<<grid, kSoloCts * 32, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts, lut_idx,
                                                            out_big, out_idx, count, stream_tables<uint32_t>(), stagger, trace);
     if (want_trace) {
-        std::vector<long long> h((size_t)rows * kSoloCts);
+        std::vector<long long> h(trace_words);
         FSC_CUDA_CHECK(cudaStreamSynchronize(st));
         FSC_CUDA_CHECK(cudaMemcpy(h.data(), trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(trace);
@@ -357,6 +372,15 @@ static void launch_pbs_solo_t(const void* bsk_f, const uint64_t* in_small, int n
             fprintf(stderr, "solo trace step %4d:", r * 64);
             for (int w = 0; w < kSoloCts; ++w) fprintf(stderr, " %9lld", h[(size_t)r * kSoloCts + w] - h[(size_t)r * kSoloCts]);
             if (r) fprintf(stderr, "   (cycles per step of warp 0: %lld)", (h[(size_t)r * kSoloCts] - h[(size_t)(r - 1) * kSoloCts]) / 64);
+            fprintf(stderr, "\n");
+        }
+        static const char* const kPhase[] = {"start", "head0", "turn", "pass", "xpose", "turn", "pass", "park", "head1", "turn", "pass", "xpose", "turn", "pass",
+                                             "product", "turn", "pass", "xpose", "turn", "pass", "tail1", "reload", "turn", "pass", "xpose", "turn", "pass", "tail0"};
+        for (int wq = 0; wq < 2; ++wq) {
+            const long long* s0 = h.data() + (size_t)rows * kSoloCts + wq * 32;
+            if (!s0[0]) continue;
+            fprintf(stderr, "solo phases, warp %d, step 512 (cycles):", wq * 4);
+            for (int k = 1; k < 28 && s0[k]; ++k) fprintf(stderr, " %s %lld", kPhase[k], s0[k] - s0[k - 1]);
             fprintf(stderr, "\n");
         }
     }
