@@ -563,8 +563,9 @@ def main():
                          "peak_nominal": FP64_NOMINAL_TF, "frac_vs_nominal": achieved_tf / FP64_NOMINAL_TF,
                          "traffic": traffic, "traffic_source": NCU_TRAFFIC_SOURCE if traffic else None,
                          "kernel": kernel_name, "ms_per_launch": ms_pbs, "flops_per_pbs": F,
-                         "peak_source": "measured in this run (fsc_measure_fp64_peak: 8 FMA chains, 512 FMAs per loop trip; MEASURED_PEAKS.json has no FP64 "
-                                        "figure); peak_nominal = 148 SM x 64 FMA/clk x 2 x 1.965 GHz",
+                         "peak_source": "measured in this run (fsc_measure_fp64_peak: 16 FMA chains per thread, two fresh operand pairs per DFMA, 512 FMAs per loop "
+                                        "trip, 4 warps per SM sub-partition - the highest-reading pattern of tools/ubench/fp64_operands.cu; MEASURED_PEAKS.json has "
+                                        "no FP64 figure); peak_nominal = 148 SM x 64 FMA/clk x 2 x 1.965 GHz",
                          "keyswitch_ms_per_launch": ms_ks,
                          "hbm": {"achieved": hbm_bytes / (ms_pbs * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": hbm_bytes / (ms_pbs * 1e-3) / 1e9 / hbm_peak,

@@ -616,7 +616,7 @@ fsc_status fsc_measure_fp64_peak(fsc_ctx* ctx, double* tflops) {
     cudaError_t err = cudaSuccess;
     for (int rep = 0; rep < 4 && err == cudaSuccess; ++rep) {          // first repetition warms up
         err = cudaEventRecord(e->ev0, e->stream);
-        fmas = fsc::launch_fp64_peak(sink, e->sm_count, 1024, e->stream); ++e->launches;
+        fmas = fsc::launch_fp64_peak(sink, e->sm_count, 2048, e->stream); ++e->launches;
         if (err == cudaSuccess) err = cudaGetLastError();
         if (err == cudaSuccess) err = cudaEventRecord(e->ev1, e->stream);
         if (err == cudaSuccess) err = cudaEventSynchronize(e->ev1);

@@ -730,27 +730,31 @@ void launch_pbs(int variant, int acc_bits, const void* bsk_f, const uint64_t* in
 
 // ---------------------------------------------------------------------------------------
 // FP64 FMA peak probe (the roofline denominator north_star asks for; MEASURED_PEAKS.json has no FP64
-// figure).  8 independent FMA chains per thread, 512 FMAs per loop trip (the loop's compare / branch / counter are
-// 0.6 % of the issue slots), 4 CTAs x 256 threads per SM.
+// figure).  16 independent FMA chains per thread, each reading its own multiplier register (two fresh 64-bit operand
+// pairs per DFMA: the pattern that measures highest on this part, tools/ubench/fp64_operands.cu - 36.1 TFLOP/s against
+// 34.0 for chains that share both other operands), 512 FMAs per loop trip, 4 warps per SM sub-partition.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters, double a, double b) {
-    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+__global__ void __launch_bounds__(128) fp64_peak_kernel(double* sink, int iters, double a, double b) {
+    double x[16], y[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { x[u] = threadIdx.x + u; y[u] = a + 1e-12 * (threadIdx.x + u); }
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int u = 0; u < 64; ++u) {
-            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
-        }
+        for (int r = 0; r < 32; ++r)
+#pragma unroll
+            for (int u = 0; u < 16; ++u) x[u] = fma(x[u], y[u], b);
     }
-    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    double s = 0;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) s += x[u];
     if (s == 12345.678) sink[0] = s;      // never true; keeps the chains alive
 }
 
 // returns the number of FMAs executed
 double launch_fp64_peak(double* sink, int sm_count, int iters, cudaStream_t st) {
-    const int blocks = sm_count * 4;
-    fp64_peak_kernel<<<blocks, 256, 0, st>>>(sink, iters, 0.999999, 1e-9);
-    return (double)blocks * 256.0 * (double)iters * 512.0;
+    const int blocks = sm_count * 4;      // 4 CTAs x 128 threads per SM: 4 warps per sub-partition
+    fp64_peak_kernel<<<blocks, 128, 0, st>>>(sink, iters, 0.999999, 1e-9);
+    return (double)blocks * 128.0 * (double)iters * 512.0;
 }
 
 void launch_negacyclic_mul(const uint64_t* a, const int64_t* b, uint64_t* c, int count, cudaStream_t st) {
