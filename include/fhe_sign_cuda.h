@@ -194,7 +194,8 @@ fsc_status fsc_set_level_exchange(fsc_ctx *ctx, int32_t rank, int32_t world, siz
  *   3. every rank: fsc_peer_pool_connect(ctx, rank, world, min_width, all_handles)   (handles in rank order)
  * Contract as above: SPMD (identical operator sequence and identical input ciphertexts on every rank), keys
  * replicated; the pool cannot grow past capacity_blocks once exported (FSC_ERR_OOM).  A peer that never arrives
- * makes the barrier give up after a few seconds; the next download reports FSC_ERR_COMM.                       */
+ * makes the barrier give up after a few seconds; the next download reports FSC_ERR_COMM.  Handles are TRUSTED input (they carry
+ * device addresses): exchange them only between the ranks of one job.                                                     */
 #define FSC_PEER_HANDLE_BYTES 128
 fsc_status fsc_peer_pool_export(fsc_ctx *ctx, size_t capacity_blocks, uint8_t *handle_out);
 fsc_status fsc_peer_pool_connect(fsc_ctx *ctx, int32_t rank, int32_t world, size_t min_width, const uint8_t *handles);
