@@ -56,6 +56,12 @@ def compute_challenge(r, pubkey, message):
     return int.from_bytes(_tagged(b"BIP0340/challenge", _b32(r[0]) + _b32(pubkey[0]) + message), "big") % N
 
 
+def compute_nonce(privkey, pubkey, message, aux_rand):
+    """src/schnorr.rs:394-401 (BIP-340 nonce from the un-negated key, as the reference computes it)."""
+    t = bytes(x ^ y for x, y in zip(_b32(privkey), _tagged(b"BIP0340/aux", aux_rand)))
+    return int.from_bytes(_tagged(b"BIP0340/nonce", t + _b32(pubkey[0]) + message), "big") % N
+
+
 class Signature:
     def __init__(self, r_x, s):
         self.r_x, self.s = r_x, s
@@ -91,3 +97,13 @@ def sign_fhe_with_k0(message, k0, privkey, privkey_fhe, client_key, fused=False,
         s_fhe = s_fhe.rem_scalar(N)
     s_without_mod = s_fhe.to_biguint(client_key)
     return Signature(r[0], s_without_mod % N)
+
+
+def sign_fhe(message, aux_rand, privkey, client_key, fused=False, public_challenge=False):
+    """src/schnorr.rs:154-208: the nonce is derived from aux_rand in plaintext (:168), the private key is encrypted here
+    (:192: `BigUintFHE::new(privkey)`), then the same scalar expression as sign_fhe_with_k0 (:195 = :274).
+    Known answer (src/schnorr.rs:440-466): vector 0 -> E907831F...310536C0."""
+    pubkey = get_public_key_with_even_y(privkey)
+    k0 = compute_nonce(privkey, pubkey, message, aux_rand)
+    return sign_fhe_with_k0(message, k0, privkey, BigUintFHE.new(privkey, client_key), client_key, fused=fused,
+                            public_challenge=public_challenge)

@@ -101,6 +101,15 @@ def test_sign_fhe_with_k0_all_vectors(ck, fused):
         assert sig.to_bytes() == sm.sign_with_k0(msg, k0, d)
 
 
+def test_sign_fhe_known_answer(ck):
+    """src/schnorr.rs:440-466 (test_schnorr_fhe): sign_fhe on BIP-340 vector 0 with aux_rand = 0 gives the published signature,
+    through the faithful and through the fused schedule."""
+    expected = "E907831F80848D1069A5371B402410364BDF1C5F8307B0084C55F1CE2DCA821525F66A4A85EA8B71E482A74F382D2CE5EBEEE8FDB2172F477DF4900D310536C0"
+    for fused in (False, True):
+        sig = schnorr.sign_fhe(bytes(32), bytes(32), 3, ck, fused=fused)
+        assert sig.to_bytes().hex().upper() == expected
+
+
 def test_sign_with_the_public_challenge_variant(ck):
     """k + e*d with the challenge e handed over in plaintext (it is public: verify recomputes it) and d, k encrypted:
     fsc_radix_scalar_mul_add_wide.  Same signature bytes as the reference's plaintext twin on every signing row, and about a third

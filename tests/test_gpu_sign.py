@@ -44,6 +44,14 @@ def test_biguint_kats_on_gpu(ck):
     assert (BigUintFHE.new(a, ck) * BigUintFHE.new(b, ck)).to_biguint(ck) == a * b
 
 
+def test_sign_fhe_known_answer_on_gpu(ck):
+    """src/schnorr.rs:440-466 (test_schnorr_fhe): `sign_fhe` (nonce from aux_rand, key encrypted inside) on vector 0 gives the
+    signature the reference's test pins, on real ciphertexts."""
+    expected = "E907831F80848D1069A5371B402410364BDF1C5F8307B0084C55F1CE2DCA821525F66A4A85EA8B71E482A74F382D2CE5EBEEE8FDB2172F477DF4900D310536C0"
+    sig = schnorr.sign_fhe(bytes(32), bytes(32), 3, ck, fused=True)
+    assert sig.to_bytes().hex().upper() == expected
+
+
 def test_sign_fhe_with_k0_vector0_faithful(ck):
     """src/schnorr.rs:469-492: vector 0 (d = 3) through the reference's own op-for-op schedule."""
     v = GOLDEN[0]
