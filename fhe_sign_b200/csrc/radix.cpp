@@ -205,6 +205,11 @@ int Evaluator::scan_world() const {
 // levels instead of log2 n; propagate() takes this path only while a level stays at one ciphertext per SM.
 Radix Evaluator::propagate_radix3(const std::vector<Block>& msg, std::vector<Block>& Y, std::vector<Block>& Z, Block* carry_out) {
     // msg: clean messages of the n blocks; Y = 2 e, Z = e of the single-block states (propagate()'s first level)
+    // Variance-unit bookkeeping (the default): 4 e_a + 2 e_b + e_c on fresh blocks costs sum c^2 = 21 <= 25, so ONE encoding per
+    // position is enough (Y is the linear 2 Z, no second bootstrap): the radix-3 scan then costs one bootstrap per position and
+    // level like the radix-2 scan and is used at every width.  Linear bookkeeping (FSC_RADIX_NOISE=linear) forbids the factor 4 and
+    // keeps the two fresh encodings.
+    const bool single = noise_in_variance_units();
     const int n = (int)msg.size();
     const int n_state = (int)Z.size();
     auto join = [](int S) { return S >= 8 ? 2 : (S == 7 ? 1 : 0); };
@@ -213,6 +218,10 @@ Radix Evaluator::propagate_radix3(const std::vector<Block>& msg, std::vector<Blo
     static const LutTable l_final = make_bilut([](int e, int m) { return (m + (e == 2)) & 3; });
     static const LutTable l_inc = make_lut([](int v) { return (v + 1) & 3; });
     static const LutTable l_is2 = make_lut([](int v) { return v == 2; });
+    if (single) {
+        Y.resize(n_state);
+        for (int i = 0; i < n_state; ++i) Y[i] = Z[i] * 2;
+    }
     for (int d = 1; d < n_state; d *= 3) {
         const bool last = 3 * (long)d >= n_state;
         std::vector<Req> todo;
@@ -223,10 +232,11 @@ Radix Evaluator::propagate_radix3(const std::vector<Block>& msg, std::vector<Blo
             if (i - 2 * d >= 0) S = S + Z[i - 2 * d];
             // Z: least significant segment of a later join, or the final carry-in; Y: any other role in the next level
             todo.push_back({S, l_j1}); where.emplace_back(1, i);
-            if (!last) { todo.push_back({S, l_j2}); where.emplace_back(0, i); }
+            if (!last && !single) { todo.push_back({S, l_j2}); where.emplace_back(0, i); }
         }
         std::vector<Block> o = level(todo);
         for (size_t k = 0; k < o.size(); ++k) (where[k].first ? nZ : nY)[where[k].second] = o[k];
+        if (single) for (int i = d; i < n_state; ++i) nY[i] = nZ[i] * 2;
         Y.swap(nY); Z.swap(nZ);
     }
     // final level: add the incoming carry (prefix of the blocks below) to every message
@@ -273,10 +283,12 @@ Radix Evaluator::propagate(const std::vector<Block>& sums, Block* carry_out) {
     // Radix-3 scan for levels that stay within one ciphertext per SM even at two bootstraps per block (2 + log3 n levels
     // instead of 2 + log2 n): the 16- and 32-block operators on one GPU, everything up to 512 blocks on eight.  A narrow
     // level costs the same whatever its width, so depth is what counts there.
-    const bool radix3 = n_state > 2 && 2 * (size_t)n_state <= kBlocksPerGpuLevel * (size_t)scan_world();
+    // With variance-unit bookkeeping the radix-3 scan needs one bootstrap per position (propagate_radix3) and is used at every width.
+    const bool single = noise_in_variance_units();
+    const bool radix3 = n_state > 2 && (single || 2 * (size_t)n_state <= kBlocksPerGpuLevel * (size_t)scan_world());
     static const LutTable l_s1 = make_lut([](int v) { return v >= 4 ? 2 : (v == 3 ? 1 : 0); });       // block sum -> e
     static const LutTable l_s2 = make_lut([](int v) { return v >= 4 ? 4 : (v == 3 ? 2 : 0); });       // block sum -> 2 e
-    std::vector<Block> msg(n), st(std::max(n_state, 0)), st2(radix3 ? n_state : 0);
+    std::vector<Block> msg(n), st(std::max(n_state, 0)), st2(radix3 && !single ? n_state : 0);
     {
         std::vector<Req> todo;
         std::vector<std::pair<int, int>> where;     // (kind, index)
@@ -285,11 +297,11 @@ Radix Evaluator::propagate(const std::vector<Block>& sums, Block* carry_out) {
             else { todo.push_back({sums[i], lut_msg()}); where.emplace_back(0, i); }
         }
         for (int i = 0; i < n_state; ++i) {
-            if (sums[i].deg <= 2) { st[i] = Block::constant(0); if (radix3) st2[i] = Block::constant(0); }
+            if (sums[i].deg <= 2) { st[i] = Block::constant(0); if (radix3 && !single) st2[i] = Block::constant(0); }
             else if (!radix3) { todo.push_back({sums[i], l_state}); where.emplace_back(1, i); }
             else {
                 todo.push_back({sums[i], l_s1}); where.emplace_back(1, i);
-                todo.push_back({sums[i], l_s2}); where.emplace_back(2, i);
+                if (!single) { todo.push_back({sums[i], l_s2}); where.emplace_back(2, i); }
             }
         }
         std::vector<Block> o = level(todo);
