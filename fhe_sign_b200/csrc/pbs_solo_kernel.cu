@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kSoloCts * 32, 1) pbs_solo_kernel(const cplx* 
                                                                     int n, int base_log, const uint64_t* __restrict__ luts,
                                                                     const uint32_t* __restrict__ lut_idx, const __grid_constant__ OutDest out_big,
                                                                     const int32_t* __restrict__ out_idx, int count,
-                                                                    const cplx* __restrict__ tabs_g, int stagger, long long* __restrict__ trace) {
+                                                                    const cplx* __restrict__ tabs_g, int stagger, int pin, long long* __restrict__ trace) {
     typedef uint32_t AccT;
     constexpr int kTmSpec = 128, kTmemCols = 512;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -114,7 +114,12 @@ __global__ void __launch_bounds__(kSoloCts * 32, 1) pbs_solo_kernel(const cplx* 
     }
     // named barriers 1..8: (1 + 2 q) = turn of the first warp of sub-partition q, (2 + 2 q) = turn of the second
     const int my_turn = 1 + 2 * (warp & 3) + (warp >> 2), other_turn = 1 + 2 * (warp & 3) + (1 - (warp >> 2));
-    if (PP && warp >= 4) turn_pass(other_turn);      // the first warp of the sub-partition goes first
+    if (PP && PP < 3 && warp >= 4) turn_pass(other_turn);      // the first warp of the sub-partition goes first
+    // PP == 3: no turns; the two warps of a sub-partition are PINNED a fixed part of a step apart instead (one named barrier
+    // per step: the first warp arrives before the first pass of trip 0, the second before pass pin & 1 of trip pin >> 1),
+    // and share the FP64 pipe freely in between.
+    const int pin_code = warp < 4 ? 0 : pin;
+    const int pin_bar = 9 + (warp & 3);
     if (warp >= 4 && stagger > 0) {      // second warp of every sub-partition: half a step behind the first
         const long long t0 = clock64();
         while (clock64() - t0 < (long long)stagger) { }
@@ -211,10 +216,11 @@ __global__ void __launch_bounds__(kSoloCts * 32, 1) pbs_solo_kernel(const cplx* 
             // ---- two passes of the one routine with a transpose between them (forward: tables 0, 1; inverse: 2, 3)
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
-                if (PP) turn_wait(my_turn);
+                if (PP == 3) { if (2 * t + h == pin_code) turn_wait(pin_bar); }
+                else if (PP) turn_wait(my_turn);
                 FSC_STAMP();       // turn taken
                 pass32(X, pass_table(tabs, (t < 2 ? 0 : 2) + h, lane));
-                if (PP) turn_pass(other_turn);
+                if (PP && PP < 3) turn_pass(other_turn);
                 FSC_STAMP();       // pass done
                 if (h == 0) {
                     const int row = t < 2 ? lane : row_inv;
@@ -348,7 +354,7 @@ __global__ void __launch_bounds__(kSoloCts * 32, 1) pbs_solo_kernel(const cplx* 
 
 template <int NH, int PP>
 static void launch_pbs_solo_t(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts, const uint32_t* lut_idx,
-                              const OutDest& out_big, const int32_t* out_idx, int count, int stagger, cudaStream_t st) {
+                              const OutDest& out_big, const int32_t* out_idx, int count, int stagger, int pin, cudaStream_t st) {
     const size_t smem = (size_t)kSoloCts * kXBufDoubles * sizeof(double) + (size_t)NH * kHalfCplx * sizeof(cplx) +
                         (size_t)kTabCplx * sizeof(cplx) + 2 * NH * sizeof(uint64_t) + 16;
     ensure_dynamic_smem(reinterpret_cast<const void*>(&pbs_solo_kernel<NH, PP>), smem);
@@ -362,7 +368,7 @@ static void launch_pbs_solo_t(const void* bsk_f, const uint64_t* in_small, int n
         FSC_CUDA_CHECK(cudaMemsetAsync(trace, 0, trace_words * sizeof(long long), st));
     }
     pbs_solo_kernel<NH, PP><<<grid, kSoloCts * 32, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts, lut_idx,
-                                                           out_big, out_idx, count, stream_tables<uint32_t>(), stagger, trace);
+                                                           out_big, out_idx, count, stream_tables<uint32_t>(), stagger, pin, trace);
     if (want_trace) {
         std::vector<long long> h(trace_words);
         FSC_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -394,9 +400,10 @@ void launch_pbs_solo(const void* bsk_f, const uint64_t* in_small, int n, int bas
     static const int stagger = [] { const char* e = getenv("FSC_SOLO_STAGGER"); return e ? atoi(e) : 0; }();
     static const int nh = [] { const char* e = getenv("FSC_SOLO_NH"); return e ? atoi(e) : 4; }();
     static const int pp = [] { const char* e = getenv("FSC_SOLO_PP"); return e ? atoi(e) : 1; }();      // FP64 turn-taking: 0 off, 1 passes, 2 passes + product + tail
-#define FSC_SOLO(NH, PP) launch_pbs_solo_t<NH, PP>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, stagger, st)
-    if (nh == 3) { if (pp == 0) FSC_SOLO(3, 0); else if (pp == 1) FSC_SOLO(3, 1); else FSC_SOLO(3, 2); }
-    else { if (pp == 0) FSC_SOLO(4, 0); else if (pp == 1) FSC_SOLO(4, 1); else FSC_SOLO(4, 2); }
+    static const int pin = [] { const char* e = getenv("FSC_SOLO_PIN"); return e ? atoi(e) : 4; }();      // PP == 3: 2 * trip + pass of the second warp's pin point
+#define FSC_SOLO(NH, PP) launch_pbs_solo_t<NH, PP>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, stagger, pin, st)
+    if (nh == 3) { if (pp == 0) FSC_SOLO(3, 0); else if (pp == 1) FSC_SOLO(3, 1); else if (pp == 2) FSC_SOLO(3, 2); else FSC_SOLO(3, 3); }
+    else { if (pp == 0) FSC_SOLO(4, 0); else if (pp == 1) FSC_SOLO(4, 1); else if (pp == 2) FSC_SOLO(4, 2); else FSC_SOLO(4, 3); }
 #undef FSC_SOLO
 }
 

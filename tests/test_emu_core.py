@@ -160,3 +160,43 @@ def test_split_blind_rotation_matches_stream_formulation(emu2, emu3, orc, oracle
     e3 = (K.phase_big(out) - K.encode(table[m])).astype(np.int64).astype(np.float64)
     e2 = (K.phase_big(out2) - K.encode(table[m])).astype(np.int64).astype(np.float64)
     assert e3.std() < 1.5 * e2.std()
+
+
+# ---- quad formulation: the split form for wide batches (pbs_core4.cuh, tests/emu/pbs_emu4.cpp) ---------------------------
+@pytest.fixture(scope="module")
+def emu4():
+    so = os.path.join(HERE, "emu", "libpbs_emu4.so")
+    src = os.path.join(HERE, "emu", "pbs_emu4.cpp")
+    cores = [os.path.join(HERE, "..", "fhe_sign_b200", "csrc", f) for f in ("pbs_core.cuh", "pbs_core2.cuh", "pbs_core3.cuh", "pbs_core4.cuh")]
+    if not os.path.exists(so) or max(os.path.getmtime(f) for f in [src] + cores) > os.path.getmtime(so):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-march=x86-64-v3", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
+    E = C.CDLL(so)
+    vp = C.c_void_p
+    E.emu4_blind_rotate.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
+    return E
+
+
+def test_quad_transpose_swizzle_is_conflict_free(emu4):
+    """[32][32] complex with physical column = column ^ row: no two lanes of a quarter warp share a 16-byte bank group,
+    for the row stores and for both kinds of column loads."""
+    assert emu4.emu4_transpose_conflicts() == 1
+
+
+def test_quad_blind_rotation_matches_stream_formulation(emu2, emu4, orc, oracle_keys, rng):
+    """Whole level-1 butterflies + the 8-value join, the [parity][index] accumulator columns and the neighbouring-slot
+    product are the stream formulation's arithmetic in another order of ownership: same decrypted values, same noise."""
+    K = oracle_keys("toy")
+    n = K.params.lwe_dim
+    bf = np.empty(n * 32 * 4 * 32 * 2, dtype=np.float64)
+    emu2.emu2_convert_bsk(n, P(K.bsk), P(bf))
+    table = rng.integers(0, 16, 16).astype(np.uint64)
+    lut = K.make_lut(table)
+    m = rng.integers(0, 16, 32).astype(np.uint64)
+    small = K.keyswitch(K.encrypt_msgs(m))
+    out, out2 = np.empty((m.size, 2049), dtype=np.uint64), np.empty((m.size, 2049), dtype=np.uint64)
+    emu4.emu4_blind_rotate(n, K.params.pbs_base_log, P(bf), P(small), m.size, P(lut), P(out))
+    emu2.emu2_blind_rotate(32, n, K.params.pbs_base_log, P(bf), P(small), m.size, P(lut), P(out2))
+    assert (K.decrypt_msgs(out) == table[m]).all()
+    e4 = (K.phase_big(out) - K.encode(table[m])).astype(np.int64).astype(np.float64)
+    e2 = (K.phase_big(out2) - K.encode(table[m])).astype(np.int64).astype(np.float64)
+    assert e4.std() < 1.5 * e2.std()
