@@ -24,6 +24,7 @@ struct Engine {
     void* bsk_f = nullptr;          // Fourier bootstrapping key [n][32 r][4 g][32 lane] complex f64, r in the order of pbs_variant
     void* bsk_s = nullptr;          // second copy in the stream kernel's order (pbs_variant 3 only)
     int pbs_variant = 3;            // 0 pair, 1 ring, 2 stream, 3 ring for wide batches + stream / split for narrow levels, 4 split: decided at key upload
+    bool wide_tx = true;            // variant 3, 32-bit accumulator: wide batches run on pbs_stream_tx_kernel<2> (FSC_PBS_WIDE=ring: pbs_ring_kernel)
     bool use_split = true;          // variant 3: levels of at most one ciphertext per SM run on pbs_split_kernel (FSC_PBS_SPLIT=0: stream kernel)
     uint64_t* ksk = nullptr;        // [kN][l_ks][n+1]
     uint8_t* ksk_limbs = nullptr;   // byte-limb transpose of the KSK for the tensor-core keyswitch [8(n+1) padded][kN*l_ks]

@@ -73,6 +73,7 @@ Engine::Engine(const fsc_params& prm, int device, uintptr_t ext_stream) : p(prm)
     pbs_init_constants();
     const char* kv = getenv("FSC_KS_VARIANT");      // "simt" | "mma" (default)
     ks_variant = (kv && kv[0] == 's') ? 0 : (kv && kv[0] == 'm') ? 1 : 2;      // simt | mma | umma (default)
+    if (const char* wk = getenv("FSC_PBS_WIDE")) wide_tx = wk[0] != 'r';         // "ring": wide batches stay on the ring kernel (comparison)
     if (const char* ns = getenv("FSC_PBS_SPLIT")) use_split = atoi(ns) != 0;      // 0: narrow levels stay on the stream kernel
     if (const char* hw = getenv("FSC_HOST_CHUNK_WAVES")) host_chunk_waves = (size_t)atoi(hw);      // 0: one chunk, copies not overlapped
 }
@@ -278,6 +279,11 @@ void Engine::pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut
         launch_pbs_quad(bsk_s, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, od, out_idx_dev, (int)count, stream);
     else if (pbs_variant == 2)
         launch_pbs_stream((int)p.acc_bits, bsk_f, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, od,
+                          out_idx_dev, (int)count, sm_count, stream);
+    else if (pbs_variant == 3 && p.acc_bits == 32 && wide_tx)
+        // wide batches, 32-bit accumulator: the stream formulation with tensor memory, straight-line trips, the two uniform
+        // passes specialised (pbs_stream_tx_kernel<2>: 83.5 k PBS/s against 77.7 k for the ring kernel, profiles/README.md)
+        launch_pbs_stream((int)p.acc_bits, bsk_s, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, od,
                           out_idx_dev, (int)count, sm_count, stream);
     else
         launch_pbs(pbs_variant, (int)p.acc_bits, bsk_f, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, od,
@@ -603,6 +609,7 @@ fsc_status fsc_launch_count(const fsc_ctx* ctx, uint64_t* out) {
 const char* fsc_pbs_kernel_name(const fsc_ctx* ctx) {
     if (!ctx) return "";
     const int v = ctx->eng->bsk_f ? ctx->eng->pbs_variant : fsc::pbs_variant_for((int)ctx->eng->p.acc_bits);
+    if (v == 3 && ctx->eng->p.acc_bits == 32 && ctx->eng->wide_tx) return "pbs_stream_tx_kernel";
     return v == 6 ? "pbs_quad_kernel" : v == 5 ? "pbs_solo_kernel" : v == 4 ? "pbs_split_kernel" : v == 2 ? "pbs_stream_kernel" : v == 0 ? "pbs_pair_kernel" : "pbs_ring_kernel";
 }
 

@@ -106,6 +106,72 @@ FSC_HD void pass32(cplx (&v)[32], const SP& sp) {
     }
 }
 
+// pass32 for a UNIFORM table (every lane the same constants: pass 0, g = 32, and pass 2, g = 0) with the root parameter G a
+// compile-time value, so that the structure of the constants is visible to the compiler:
+//   * node exponent 0 (s = 1; the odd node is i): the butterfly is four additions — all of level 1 and 2 and one constant of
+//     each later level for G = 0 (a plain radix-2 DFT: 124 of 512 instructions go away);
+//   * node exponent 512 (tan = 1): the two rotations are additions;
+//   * level 1 of G = 32 is exponent 512: tangent form, 6 instructions instead of 8;
+//   * sp.get(ci) reads a __constant__ table in the kernels: the remaining constants are constant-bank operands of the DFMAs
+//     (no register operand, no shared-memory load) — the same arithmetic, in the same order, as pass32 wherever the constant
+//     is not special.
+template <int G, class SP>
+FSC_HD void pass32_uniform(cplx (&v)[32], const SP& sp) {
+    static_assert(G == 0 || G == 32, "uniform tables: g = 0 (inverse pass A) or g = 32 (forward pass 1)");
+    if (G == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const cplx lo = v[j], hi = v[16 + j];
+            v[j].x = lo.x + hi.x;      v[j].y = lo.y + hi.y;
+            v[16 + j].x = lo.x - hi.x; v[16 + j].y = lo.y - hi.y;
+        }
+    } else {      // s = exp(i pi / 4) = c (1 + i)
+        const double c = sp.get(0).x;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const cplx lo = v[j], hi = v[16 + j];
+            const double qx = hi.x - hi.y, qy = hi.x + hi.y;
+            v[j].x = fma(c, qx, lo.x);       v[j].y = fma(c, qy, lo.y);
+            v[16 + j].x = fma(-c, qx, lo.x); v[16 + j].y = fma(-c, qy, lo.y);
+        }
+    }
+#pragma unroll
+    for (int L = 2; L <= 5; ++L) {
+        const int half = 16 >> (L - 1);
+#pragma unroll
+        for (int m = 0; m < (1 << (L - 1)); ++m) {
+            const int base = m * 2 * half;
+            const bool odd = m & 1;
+            const int ci = (1 << (L - 2)) + (m >> 1);
+            const int e = node_exponent(ci, G) & 4095;
+            const cplx s = sp.get(ci);      // (w, t)
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+                const cplx lo = v[base + j], hi = v[base + half + j];
+                if (e == 0) {
+                    if (!odd) {
+                        v[base + j].x = lo.x + hi.x;        v[base + j].y = lo.y + hi.y;
+                        v[base + half + j].x = lo.x - hi.x; v[base + half + j].y = lo.y - hi.y;
+                    } else {
+                        v[base + j].x = lo.x - hi.y;        v[base + j].y = lo.y + hi.x;
+                        v[base + half + j].x = lo.x + hi.y; v[base + half + j].y = lo.y - hi.x;
+                    }
+                } else {
+                    const double qx = (e == 512) ? hi.x - hi.y : fma(-s.y, hi.y, hi.x);
+                    const double qy = (e == 512) ? hi.x + hi.y : fma(s.y, hi.x, hi.y);
+                    if (!odd) {
+                        v[base + j].x = fma(s.x, qx, lo.x);         v[base + j].y = fma(s.x, qy, lo.y);
+                        v[base + half + j].x = fma(-s.x, qx, lo.x); v[base + half + j].y = fma(-s.x, qy, lo.y);
+                    } else {
+                        v[base + j].x = fma(-s.x, qy, lo.x);        v[base + j].y = fma(s.x, qx, lo.y);
+                        v[base + half + j].x = fma(s.x, qy, lo.x);  v[base + half + j].y = fma(-s.x, qx, lo.y);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // Gentleman-Sande inverse of pass32 (exact reverse up to a factor 32) reading the same table: entry 0 is (re, im),
 // entries >= 1 are (cos, tan) and are turned back into (re, im) with one multiply.  Used by the ring kernel, whose
 // inverse keeps the merged-twist Gentleman-Sande form.

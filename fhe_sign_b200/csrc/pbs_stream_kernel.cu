@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <type_traits>
+#include <mutex>
 #include <vector>
 #include "pbs_core2.cuh"
 #include "fsc_internal.h"
@@ -31,6 +32,25 @@
 #include "pbs_stream_tables.cuh"
 
 namespace fsc {
+
+// Uniform pass tables (pass 0: g = 32, pass 2: g = 0) in constant memory for pass32_uniform: the constants become
+// constant-bank operands of the DFMAs.  Written once per device by stream_uniform_constants_init().
+__constant__ cplx c_su[2][16];
+template <int Q> struct UniConsts {
+    __device__ __forceinline__ cplx get(int ci) const { return c_su[Q][ci]; }
+};
+static void stream_uniform_constants_init() {
+    static bool done[64] = {};
+    static std::mutex mu;
+    int dev = 0;
+    FSC_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[dev & 63]) return;
+    cplx h[2][16];
+    for (int ci = 0; ci < 16; ++ci) { h[0][ci] = pass_const(ci, pass_g(0, 0)); h[1][ci] = pass_const(ci, pass_g(2, 0)); }
+    FSC_CUDA_CHECK(cudaMemcpyToSymbol(c_su, h, sizeof(h)));
+    done[dev & 63] = true;
+}
 
 // forward FFT of the 32 x 32 complex points held by the warp through the shared pass (tables in global memory)
 __device__ __forceinline__ void stream_fft_fwd(int lane, double* xb, const cplx* tabs, cplx (&v)[32]) {
@@ -242,6 +262,13 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_stream_kernel(const cplx* __r
 // Shared memory keeps what crosses lanes: the accumulator copy for the rotated reads, the transposes, the key ring,
 // the per-lane pass tables.  One pair barrier hands the spectra over, one guards their reuse.
 // ---------------------------------------------------------------------------------------
+// MODE 0: one pass routine for the four passes (rolled trips).  MODE 1: the two uniform passes through pass32_uniform
+// (constants from the constant bank, trivial constants as additions: 2 688 -> 2 532 FP64 instructions), trips rolled with a
+// switch on the pass; MODE 2: the same, straight-line trips.
+#ifndef FSC_TX_ST
+#define FSC_TX_ST 2      // spectrum stores of MODE 2: 2 = one double per tcgen05.st, 4 = one complex, 16 = four complex (gathered)
+#endif
+template <int MODE>
 __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                                  int n, int base_log, const uint64_t* __restrict__ luts,
                                                                  const uint32_t* __restrict__ lut_idx, const __grid_constant__ OutDest out_big,
@@ -251,10 +278,17 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
     constexpr int CTS = 4, NH = 2;
     constexpr int kTmAcc = 256, kTmTwist = 384, kTmemCols = 512;
     constexpr int kTabNoTwist = kTabTwist;               // the twist table lives in tensor memory
+    // MODE 2: the transposes move whole complex values through a [32][33] complex buffer per warp (one store phase, one load
+    // phase, 16 bytes per lane and instruction, conflict-free through the padded row), and the by-index copy of the
+    // accumulator polynomial for the rotated reads lives in the first 8 KB of that buffer (written by the tail, when the
+    // buffer is free; private to the warp): no separate accumulator array, same footprint.
+    constexpr bool WIDE = MODE == 2;
+    constexpr int kXC = 32 * 33;                         // complex per warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pair_t<AccT>* acc_all = reinterpret_cast<pair_t<AccT>*>(smem_raw);
-    double* xbuf_all = reinterpret_cast<double*>(smem_raw + (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>));
-    cplx* ring = reinterpret_cast<cplx*>(xbuf_all + (size_t)CTS * 2 * kXBufDoubles);
+    double* xbuf_all = reinterpret_cast<double*>(smem_raw + (WIDE ? 0 : (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>)));
+    cplx* ring = WIDE ? reinterpret_cast<cplx*>(smem_raw) + (size_t)CTS * 2 * kXC
+                      : reinterpret_cast<cplx*>(xbuf_all + (size_t)CTS * 2 * kXBufDoubles);
     cplx* tabs = ring + (size_t)NH * kHalfCplx;
     uint64_t* full = reinterpret_cast<uint64_t*>(tabs + kTabNoTwist);
     uint64_t* empty = full + NH;
@@ -285,7 +319,8 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
     const int c_raw = blockIdx.x * CTS + ctl;
     const bool live = c_raw < count;
     const int c = live ? c_raw : count - 1;            // padding warps shadow the last ciphertext, never store
-    pair_t<AccT>* acc = acc_all + (size_t)(ctl * 2 + p) * 1024;
+    cplx* xc = reinterpret_cast<cplx*>(smem_raw) + (size_t)(ctl * 2 + p) * kXC;      // MODE 2
+    pair_t<AccT>* acc = WIDE ? reinterpret_cast<pair_t<AccT>*>(xc) : acc_all + (size_t)(ctl * 2 + p) * 1024;
     double* xb = xbuf_all + (size_t)(ctl * 2 + p) * kXBufDoubles;
     const uint64_t* ct = in_small + (size_t)c * (n + 1);
     const uint64_t* lut = luts + (size_t)(lut_idx ? lut_idx[c] : 0) * kN;
@@ -373,16 +408,28 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
             }
         };
         auto xp_out = [&]() {
-            xp_store(lane, xb, X, 0);
+            if constexpr (WIDE) {
+                __syncwarp();      // the head's rotated reads of the by-index copy are done in every lane
+#pragma unroll
+                for (int pos = 0; pos < 32; ++pos) xc[brev5(pos) * 33 + lane] = X[pos];
+            } else {
+                xp_store(lane, xb, X, 0);
+            }
             __syncwarp();
         };
         auto xp_in = [&](int row) {
-            xp_load(row, xb, X, 0);
-            __syncwarp();
-            xp_store(lane, xb, X, 1);
-            __syncwarp();
-            xp_load(row, xb, X, 1);
-            __syncwarp();
+            if constexpr (WIDE) {
+#pragma unroll
+                for (int s2 = 0; s2 < 32; ++s2) X[s2] = xc[row * 33 + s2];
+                __syncwarp();
+            } else {
+                xp_load(row, xb, X, 0);
+                __syncwarp();
+                xp_store(lane, xb, X, 1);
+                __syncwarp();
+                xp_load(row, xb, X, 1);
+                __syncwarp();
+            }
         };
         auto do_mac = [&]() {
             if (producer) {      // both halves of this step requested before anyone sleeps on them (see pbs_stream_kernel)
@@ -393,10 +440,21 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
             tmem_fence_after();
 #pragma unroll
             for (int k = 0; k < 8; ++k) {                    // position order: the partner reads 4 consecutive positions per load
-                cplx v4[4];
+                if constexpr (MODE == 2 && FSC_TX_ST == 4) {
 #pragma unroll
-                for (int rr = 0; rr < 4; ++rr) v4[rr] = X[brev5(freq_at(4 * k + rr))];
-                tmem_st4(t_own + 16 * k, v4);
+                    for (int rr = 0; rr < 4; ++rr) tmem_st_c1(t_own + 16 * k + 4 * rr, X[brev5(freq_at(4 * k + rr))]);
+                } else if constexpr (MODE == 2 && FSC_TX_ST == 2) {
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        tmem_st_d1(t_own + 16 * k + 4 * rr, X[brev5(freq_at(4 * k + rr))].x);
+                        tmem_st_d1(t_own + 16 * k + 4 * rr + 2, X[brev5(freq_at(4 * k + rr))].y);
+                    }
+                } else {
+                    cplx v4[4];
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) v4[rr] = X[brev5(freq_at(4 * k + rr))];
+                    tmem_st4(t_own + 16 * k, v4);
+                }
             }
             tmem_wait_st();
             tmem_fence_before();
@@ -468,18 +526,30 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
             tmem_wait_st();
             __syncwarp();
         };
-#ifdef FSC_STREAM_TX_UNROLL
-#pragma unroll
-#else
+        if constexpr (MODE == 2) {
+            do_head();
+            pass32_uniform<32>(X, UniConsts<0>{});
+            xp_out();
+            xp_in(lane);
+            pass32(X, pass_table(tabs, 1, lane));
+            do_mac();
+            pass32_uniform<0>(X, UniConsts<1>{});
+            xp_out();
+            xp_in(row_inv);
+            pass32(X, pass_table(tabs, 3, lane));
+            do_tail();
+        } else {
 #pragma unroll 1
-#endif
-        for (int q = 0; q < 4; ++q) {
-            if (q == 0) do_head();
-            else if (q & 1) xp_in(q == 1 ? lane : row_inv);
-            pass32(X, pass_table(tabs, q, lane));
-            if (!(q & 1)) xp_out();
-            else if (q == 1) do_mac();
-            else do_tail();
+            for (int q = 0; q < 4; ++q) {
+                if (q == 0) do_head();
+                else if (q & 1) xp_in(q == 1 ? lane : row_inv);
+                if (MODE == 1 && q == 0) pass32_uniform<32>(X, UniConsts<0>{});
+                else if (MODE == 1 && q == 2) pass32_uniform<0>(X, UniConsts<1>{});
+                else pass32(X, pass_table(tabs, q, lane));
+                if (!(q & 1)) xp_out();
+                else if (q == 1) do_mac();
+                else do_tail();
+            }
         }
         if (producer) prod.poll(lane, bsk_f, ring, full, empty, total_halves);
     }
@@ -487,8 +557,11 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
 
     if (live) {
         const size_t out = (size_t)(out_idx ? out_idx[c] : c) * (kN + 1);
-        const pair_t<AccT>* mask = acc_all + (size_t)(ctl * 2) * 1024;
-        for (int j = (p * 32 + lane); j <= kN; j += 64) store_out_word(out_big, out + j, extract_word<AccT>(mask, mask + 1024, j));
+        const pair_t<AccT>* mask = WIDE ? reinterpret_cast<const pair_t<AccT>*>(reinterpret_cast<cplx*>(smem_raw) + (size_t)(ctl * 2) * kXC)
+                                        : acc_all + (size_t)(ctl * 2) * 1024;
+        const pair_t<AccT>* body = WIDE ? reinterpret_cast<const pair_t<AccT>*>(reinterpret_cast<cplx*>(smem_raw) + (size_t)(ctl * 2 + 1) * kXC)
+                                        : mask + 1024;
+        for (int j = (p * 32 + lane); j <= kN; j += 64) store_out_word(out_big, out + j, extract_word<AccT>(mask, body, j));
     }
     tmem_fence_before();
     __syncthreads();
@@ -561,11 +634,17 @@ static void launch_pbs_stream_t(const void* bsk_f, const uint64_t* in_small, int
 
 static void launch_pbs_stream_tx(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
                                  const uint32_t* lut_idx, const OutDest& out_big, const int32_t* out_idx, int count, cudaStream_t st) {
-    const size_t smem = (size_t)4 * 2 * 1024 * sizeof(pair_t<uint32_t>) + (size_t)4 * 2 * kXBufDoubles * sizeof(double) +
-                        (size_t)2 * kHalfCplx * sizeof(cplx) + (size_t)kTabTwist * sizeof(cplx) + 2 * 2 * sizeof(uint64_t) + 16;
-    ensure_dynamic_smem(reinterpret_cast<const void*>(&pbs_stream_tx_kernel), smem);      // per device (the opt-in is a per-device attribute)
-    pbs_stream_tx_kernel<<<(count + 3) / 4, 256, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts, lut_idx,
-                                                             out_big, out_idx, count, stream_tables<uint32_t>());
+    static const int mode = [] { const char* e = getenv("FSC_STREAM_TX"); return e ? atoi(e) : 2; }();      // 0 / 1: comparison forms
+#define FSC_TX(MODE) do { \
+    const size_t smem = (MODE == 2 ? (size_t)4 * 2 * 32 * 33 * sizeof(cplx) \
+                                   : (size_t)4 * 2 * 1024 * sizeof(pair_t<uint32_t>) + (size_t)4 * 2 * kXBufDoubles * sizeof(double)) + \
+                        (size_t)2 * kHalfCplx * sizeof(cplx) + (size_t)kTabTwist * sizeof(cplx) + 2 * 2 * sizeof(uint64_t) + 16; \
+    ensure_dynamic_smem(reinterpret_cast<const void*>(&pbs_stream_tx_kernel<MODE>), smem); \
+    pbs_stream_tx_kernel<MODE><<<(count + 3) / 4, 256, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts, lut_idx, \
+                                                                   out_big, out_idx, count, stream_tables<uint32_t>()); } while (0)
+    if (mode) stream_uniform_constants_init();
+    if (mode == 2) FSC_TX(2); else if (mode == 1) FSC_TX(1); else FSC_TX(0);
+#undef FSC_TX
 }
 
 // Configuration by batch width: wide levels pack 4 (u32 accumulator) or 3 (u64) ciphertexts per CTA so that one key

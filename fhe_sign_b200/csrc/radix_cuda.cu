@@ -196,14 +196,38 @@ public:
             return;
         }
         peer_dirty = true;      // local work since the last barrier: a peer must not overwrite slots this level may still read
+        static const bool trace = getenv("FSC_LEVEL_TRACE") != nullptr;      // diagnostic: width and device time of every level (synchronises)
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (trace) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, eng->stream); }
+        struct TraceEnd {
+            cudaEvent_t a, b; cudaStream_t st; size_t w;
+            ~TraceEnd() {
+                if (!a) return;
+                cudaEventRecord(b, st); cudaEventSynchronize(b);
+                float ms = 0; cudaEventElapsedTime(&ms, a, b);
+                fprintf(stderr, "level trace: width %zu %.3f ms (%.0f PBS/s)\n", w, ms, w / (ms * 1e-3));
+                cudaEventDestroy(a); cudaEventDestroy(b);
+            }
+        } trace_end{e0, e1, eng->stream, reqs.size()};
         ensure_stage_big(reqs.size());
         eng->ensure_scratch(reqs.size());
         const Csr c = upload(reqs, true);
+        cudaEvent_t t1 = nullptr, t2 = nullptr, t3 = nullptr, t4 = nullptr;
+        if (trace) { cudaEventCreate(&t1); cudaEventCreate(&t2); cudaEventCreate(&t3); cudaEventCreate(&t4); cudaEventRecord(t1, eng->stream); }
         launch_lincomb(pool, c.row_ptr, c.slot, c.coef, c.cst, delta, stage_big, nullptr, (int)c.count, (int)words, eng->stream);
         ++eng->launches;
         FSC_CUDA_CHECK(cudaGetLastError());
+        if (trace) cudaEventRecord(t2, eng->stream);
         eng->keyswitch(stage_big, eng->scratch_small, c.count);
+        if (trace) cudaEventRecord(t3, eng->stream);
         eng->pbs(eng->scratch_small, &luts, c.lut, pool, c.count, c.dst);
+        if (trace) {
+            cudaEventRecord(t4, eng->stream); cudaEventSynchronize(t4);
+            float a = 0, b = 0, d = 0, h = 0;
+            cudaEventElapsedTime(&h, e0, t1); cudaEventElapsedTime(&a, t1, t2); cudaEventElapsedTime(&b, t2, t3); cudaEventElapsedTime(&d, t3, t4);
+            fprintf(stderr, "   host prep + index upload %.3f ms | linear combinations %.3f | keyswitch %.3f | blind rotation %.3f\n", h, a, b, d);
+            cudaEventDestroy(t1); cudaEventDestroy(t2); cudaEventDestroy(t3); cudaEventDestroy(t4);
+        }
     }
     // this rank bootstraps its contiguous slice into the exchange buffer, all ranks all-gather, every rank scatters
     void run_level_sharded(const std::vector<LevelReq>& reqs) {

@@ -133,6 +133,18 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const cplx (&v)[4]) {
                  ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]),
                  "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]) : "memory");
 }
+// one complex double <-> 4 consecutive columns, one double <-> 2: the operands are the value's own register pair(s), so ptxas
+// need not gather sixteen words into consecutive registers first (16 IMAD.MOV per x16 store, profiles/r02q_*)
+__device__ __forceinline__ void tmem_st_c1(uint32_t taddr, const cplx& v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__double2loint(v.x)), "r"(__double2hiint(v.x)),
+                 "r"(__double2loint(v.y)), "r"(__double2hiint(v.y)) : "memory");
+}
+__device__ __forceinline__ void tmem_st_d1(uint32_t taddr, double v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__double2loint(v)), "r"(__double2hiint(v)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_d1(uint32_t taddr, uint32_t (&w)[2]) {      // tmem_wait_ld() before use
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(taddr) : "memory");
+}
 // raw 32-bit columns of the calling thread's lane
 __device__ __forceinline__ void tmem_ldw4(uint32_t taddr, uint32_t (&w)[4]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(taddr) : "memory");

@@ -22,9 +22,15 @@ struct Tables {
 };
 const Tables& tables() { static Tables T; return T; }
 
+int g_uniform = 0;      // 1: the uniform passes (q = 0, 2) through pass32_uniform (what pbs_stream_tx_kernel<1..2> runs)
 void run_pass(int q, cplx (*v)[32]) {
     const Tables& T = tables();
-    for (int l = 0; l < 32; ++l) pass32(v[l], StridedConsts{&T.t[q][0][l], 32});
+    for (int l = 0; l < 32; ++l) {
+        const StridedConsts sp{&T.t[q][0][l], 32};
+        if (g_uniform && q == 0) pass32_uniform<32>(v[l], sp);
+        else if (g_uniform && q == 2) pass32_uniform<0>(v[l], sp);
+        else pass32(v[l], sp);
+    }
 }
 void transpose(cplx (*v)[32], bool inverse) {
     std::vector<double> xb(kXBufDoubles);
@@ -85,6 +91,7 @@ void blind_rotate(int n, int base_log, const cplx* bsk_f, const uint64_t* ct, co
 }  // namespace
 
 extern "C" {
+void emu2_set_uniform(int on) { g_uniform = on; }
 // standard-domain BSK [n][2][1][2][2048] -> Fourier layout [n][32 position][4 g][32 lane]
 void emu2_convert_bsk(int n, const uint64_t* bsk, double* out_f) {
     cplx* o = reinterpret_cast<cplx*>(out_f);

@@ -77,6 +77,7 @@ def emu2():
     E.emu2_convert_bsk.argtypes = [C.c_int, vp, vp]
     E.emu2_blind_rotate.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]
     E.emu2_min_cos.restype = C.c_double
+    E.emu2_set_uniform.argtypes = [C.c_int]
     return E
 
 
@@ -90,6 +91,37 @@ def test_stream_frequency_order_is_closed_under_bit_reversal():
     for c in range(8):
         chunk = seq[4 * c:4 * c + 4]
         assert sorted(chunk) == sorted(brev5(x) for x in chunk)
+
+
+@pytest.mark.parametrize("acc_bits", [64, 32])
+def test_stream_uniform_passes_specialised(emu2, orc, oracle_keys, rng, acc_bits):
+    """pass32_uniform (compile-time root parameter: trivial constants as additions, tangent level 1) is pass32 on the uniform
+    tables up to the rounding of the multiplications it removes: exact products agree, the blind rotation decrypts, same noise."""
+    a = rng.integers(0, 2**64, 2048, dtype=np.uint64)
+    b = rng.integers(-2**22, 2**22, 2048, dtype=np.int64)
+    c = np.empty_like(a)
+    K = oracle_keys("toy")
+    n = K.params.lwe_dim
+    bf = np.empty(n * 32 * 4 * 32 * 2, dtype=np.float64)
+    emu2.emu2_convert_bsk(n, P(K.bsk), P(bf))
+    table = rng.integers(0, 16, 16).astype(np.uint64)
+    lut = K.make_lut(table)
+    m = rng.integers(0, 16, 128).astype(np.uint64)
+    small = K.keyswitch(K.encrypt_msgs(m))
+    out, out0 = np.empty((m.size, 2049), dtype=np.uint64), np.empty((m.size, 2049), dtype=np.uint64)
+    emu2.emu2_blind_rotate(acc_bits, n, K.params.pbs_base_log, P(bf), P(small), m.size, P(lut), P(out0))
+    emu2.emu2_set_uniform(1)
+    try:
+        emu2.emu2_negacyclic_mul(P(a), P(b), P(c))
+        emu2.emu2_blind_rotate(acc_bits, n, K.params.pbs_base_log, P(bf), P(small), m.size, P(lut), P(out))
+    finally:
+        emu2.emu2_set_uniform(0)
+    d = (c - orc.negacyclic_mul_exact(a, b)).astype(np.int64)
+    assert np.abs(d).max() < 2**43
+    assert (K.decrypt_msgs(out) == table[m]).all()
+    e1 = (K.phase_big(out) - K.encode(table[m])).astype(np.int64).astype(np.float64)
+    e0 = (K.phase_big(out0) - K.encode(table[m])).astype(np.int64).astype(np.float64)
+    assert e1.std() < 1.3 * e0.std(), (e1.std(), e0.std())
 
 
 def test_stream_tangent_constants_are_finite(emu2):
