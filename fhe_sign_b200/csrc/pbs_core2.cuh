@@ -66,7 +66,10 @@ FSC_HD constexpr int freq_pos(int k1) {            // k1 -> position
 
 // ---- the pass ------------------------------------------------------------------------------
 // SP::get(ci) returns table entry ci of the calling lane.
-template <class SP>
+// L1TAN: table entry 0 holds (cos, tan) like the other entries and level 1 runs in the tangent form too (6 instructions per
+// butterfly instead of 8).  Only for tables whose level-1 constant has cos != 0 in every lane: pass 1 (g = 4 lane + 1,
+// min |cos| = 0.0245); pass 3 meets s = -i in lane 16 and keeps the (re, im) form.
+template <bool L1TAN = false, class SP>
 FSC_HD void pass32(cplx (&v)[32], const SP& sp) {
     {   // level 1: (re, im) constant
         provider_begin_level(sp, 1);
@@ -74,10 +77,17 @@ FSC_HD void pass32(cplx (&v)[32], const SP& sp) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const cplx lo = v[j], hi = v[16 + j];
-            const double tx = fma(-s.y, hi.y, s.x * hi.x);
-            const double ty = fma(s.y, hi.x, s.x * hi.y);
-            v[j].x = lo.x + tx;      v[j].y = lo.y + ty;
-            v[16 + j].x = lo.x - tx; v[16 + j].y = lo.y - ty;
+            if (L1TAN) {
+                const double qx = fma(-s.y, hi.y, hi.x);
+                const double qy = fma(s.y, hi.x, hi.y);
+                v[j].x = fma(s.x, qx, lo.x);       v[j].y = fma(s.x, qy, lo.y);
+                v[16 + j].x = fma(-s.x, qx, lo.x); v[16 + j].y = fma(-s.x, qy, lo.y);
+            } else {
+                const double tx = fma(-s.y, hi.y, s.x * hi.x);
+                const double ty = fma(s.y, hi.x, s.x * hi.y);
+                v[j].x = lo.x + tx;      v[j].y = lo.y + ty;
+                v[16 + j].x = lo.x - tx; v[16 + j].y = lo.y - ty;
+            }
         }
     }
 #pragma unroll

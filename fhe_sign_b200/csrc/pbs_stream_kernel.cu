@@ -265,6 +265,12 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_stream_kernel(const cplx* __r
 // MODE 0: one pass routine for the four passes (rolled trips).  MODE 1: the two uniform passes through pass32_uniform
 // (constants from the constant bank, trivial constants as additions: 2 688 -> 2 532 FP64 instructions), trips rolled with a
 // switch on the pass; MODE 2: the same, straight-line trips.
+#ifndef FSC_TX_I2F
+#define FSC_TX_I2F 1     // head of MODE 2: int -> double through the conversion unit (1) or the mantissa trick (0)
+#endif
+#ifndef FSC_TX_F2I
+#define FSC_TX_F2I 1     // tail of MODE 2: rounding to the accumulator through the conversion unit (1) or to_torus32 (0)
+#endif
 #ifndef FSC_TX_ST
 #define FSC_TX_ST 2      // spectrum stores of MODE 2: 2 = one double per tcgen05.st, 4 = one complex, 16 = four complex (gathered)
 #endif
@@ -302,6 +308,7 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
     for (int t = threadIdx.x; t < kTabNoTwist; t += CTS * 64) {
         const double2 d = __ldg(reinterpret_cast<const double2*>(tabs_g + t));
         tabs[t].x = d.x; tabs[t].y = d.y;
+        if (MODE == 2 && t >= kTabL1 && t < kTabL1 + 32) tabs[t].y = d.y / d.x;      // pass 1, level 1: (cos, tan) for pass32<true>
     }
     if (warp == 0) tmem_alloc<kTmemCols>(tmem_slot);
     tmem_fence_before();
@@ -402,8 +409,15 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
                     const int py = (int)(P.x + P.y) - px;
                     const int dx = imad(px, sx, half - (int)w[2 * u]);
                     const int dy = imad(py, sy, half - (int)w[2 * u + 1]);
-                    X[j2].x = __hiloint2double(0x43300000, (dx >> sh) ^ (int)0x80000000) - 4503601774854144.0;
-                    X[j2].y = __hiloint2double(0x43300000, (dy >> sh) ^ (int)0x80000000) - 4503601774854144.0;
+                    if constexpr (MODE == 2 && FSC_TX_I2F) {
+                        // wide batches are bound by the FP64 pipe: the conversion unit (quarter rate, otherwise idle) takes the
+                        // 64 int -> double conversions instead of 64 DADDs + 128 integer instructions of the mantissa trick
+                        X[j2].x = (double)(dx >> sh);
+                        X[j2].y = (double)(dy >> sh);
+                    } else {
+                        X[j2].x = __hiloint2double(0x43300000, (dx >> sh) ^ (int)0x80000000) - 4503601774854144.0;
+                        X[j2].y = __hiloint2double(0x43300000, (dy >> sh) ^ (int)0x80000000) - 4503601774854144.0;
+                    }
                 }
             }
         };
@@ -436,8 +450,11 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
                 while (prod.next_h < 2 * (i + 1) && prod.next_h < total_halves)
                     prod.poll(lane, bsk_f, ring, full, empty, total_halves);
             }
-            pair_barrier(1 + ctl);                           // the partner has read the spectrum of the previous step
-            tmem_fence_after();
+            if constexpr (MODE != 2) {
+                pair_barrier(1 + ctl);                       // the partner has read the spectrum of the previous step
+                tmem_fence_after();
+            }      // MODE 2: that barrier sits at the end of the previous product, where the two warps are in step anyway, so
+                   // that the spectrum stores below can be scheduled into the last butterfly level of the pass before them
 #pragma unroll
             for (int k = 0; k < 8; ++k) {                    // position order: the partner reads 4 consecutive positions per load
                 if constexpr (MODE == 2 && FSC_TX_ST == 4) {
@@ -496,6 +513,10 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
             tmem_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(empty + st0); mbar_arrive(empty + st1); }
+            if constexpr (MODE == 2) {
+                pair_barrier(1 + ctl);                       // both warps have read each other's spectrum: it may be overwritten
+                tmem_fence_after();
+            }
         };
         auto do_tail = [&]() {
             // twist constants and own-index pairs from tensor memory; results to shared memory (rotated reads) and back
@@ -516,8 +537,15 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     pair_t<AccT> O;
-                    O.x = w[2 * u] + to_acc_scaled<AccT>(re[u]);
-                    O.y = w[2 * u + 1] + to_acc_scaled<AccT>(im[u]);
+                    if constexpr (MODE == 2 && FSC_TX_F2I) {
+                        // round(v) mod 2^32 through the conversion unit: one F2I.S64 (|v| is 2^57 rms, 2^63 is 60 sigma away)
+                        // instead of the four DADDs of to_torus32 - the same integer, and the FP64 pipe is what bounds this kernel
+                        O.x = w[2 * u] + (uint32_t)(uint64_t)__double2ll_rn(re[u]);
+                        O.y = w[2 * u + 1] + (uint32_t)(uint64_t)__double2ll_rn(im[u]);
+                    } else {
+                        O.x = w[2 * u] + to_acc_scaled<AccT>(re[u]);
+                        O.y = w[2 * u + 1] + to_acc_scaled<AccT>(im[u]);
+                    }
                     acc[lane + 32 * tail_j2(8 * k + u)] = O;
                     w[2 * u] = O.x; w[2 * u + 1] = O.y;
                 }
@@ -531,7 +559,7 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
             pass32_uniform<32>(X, UniConsts<0>{});
             xp_out();
             xp_in(lane);
-            pass32(X, pass_table(tabs, 1, lane));
+            pass32<true>(X, pass_table(tabs, 1, lane));
             do_mac();
             pass32_uniform<0>(X, UniConsts<1>{});
             xp_out();

@@ -29,6 +29,12 @@ void run_pass(int q, cplx (*v)[32]) {
         const StridedConsts sp{&T.t[q][0][l], 32};
         if (g_uniform && q == 0) pass32_uniform<32>(v[l], sp);
         else if (g_uniform && q == 2) pass32_uniform<0>(v[l], sp);
+        else if (g_uniform && q == 1) {      // level 1 in the tangent form: entry 0 as (cos, tan), what the kernel's table copy makes of it
+            cplx t[16];
+            for (int ci = 0; ci < 16; ++ci) t[ci] = T.t[q][ci][l];
+            t[0].y = t[0].y / t[0].x;
+            pass32<true>(v[l], StridedConsts{t, 1});
+        }
         else pass32(v[l], sp);
     }
 }
