@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
                                                                  int n, int base_log, const uint64_t* __restrict__ luts,
                                                                  const uint32_t* __restrict__ lut_idx, const __grid_constant__ OutDest out_big,
                                                                  const int32_t* __restrict__ out_idx, int count,
-                                                                 const cplx* __restrict__ tabs_g) {
+                                                                 const cplx* __restrict__ tabs_g, int stagger) {
     typedef uint32_t AccT;
     constexpr int CTS = 4, NH = 2;
     constexpr int kTmAcc = 256, kTmTwist = 384, kTmemCols = 512;
@@ -374,6 +374,11 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
     int stage = 0;
     uint32_t phase = 0;
     cplx X[32];
+    if (stagger > 0) {      // experiment (FSC_TX_STAGGER): ciphertext k of the CTA starts k * stagger cycles late
+        const long long t0 = clock64();
+        while (clock64() - t0 < (long long)stagger * ctl) { }
+        __syncwarp();
+    }
     for (int i = 0; i < n; ++i) {
         if ((i & 31) == 0) a_chunk = (i + lane < n) ? modswitch(ct[i + lane]) : 0;
         const int a = __shfl_sync(0xffffffffu, a_chunk, i & 31);
@@ -390,11 +395,20 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
             const int dsx = sxB - sxA, dsy = syB - syA;
             unsigned b8 = (unsigned)(base & 1023) << 3;
             const char* pb = reinterpret_cast<const char*>(acc);
+            // MODE 2: the own-index pairs of chunk k + 1 are requested before chunk k is worked on (tcgen05.wait::ld waits for
+            // every outstanding load, so the request goes out right after the wait: its latency hides behind 8 elements)
+            uint32_t wbuf[2][16];
+            if constexpr (MODE == 2) tmem_ldw16(t_acc, wbuf[0]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                uint32_t w[16];
-                tmem_ldw16(t_acc + 16 * k, w);
-                tmem_wait_ld();
+                uint32_t (&w)[16] = wbuf[k & 1];
+                if constexpr (MODE == 2) {
+                    tmem_wait_ld();
+                    if (k < 3) tmem_ldw16(t_acc + 16 * (k + 1), wbuf[(k + 1) & 1]);
+                } else {
+                    tmem_ldw16(t_acc + 16 * k, w);
+                    tmem_wait_ld();
+                }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int j2 = tail_j2(8 * k + u);
@@ -497,11 +511,21 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
             own(std::integral_constant<int, 6>{}); own(std::integral_constant<int, 7>{});
             pair_barrier(1 + ctl);                           // the partner's spectrum is in tensor memory
             tmem_fence_after();
+            uint32_t obuf[2][16];
+            if constexpr (MODE == 2) tmem_ldw16(t_oth, obuf[0]);
             auto oth = [&](auto kc) {
                 constexpr int K = decltype(kc)::value;
                 const cplx* g = (K < 4 ? g0 : g1);
                 cplx o[4], go[4];
-                tmem_ld4(t_oth + 16 * K, o);
+                if constexpr (MODE == 2) {
+                    tmem_wait_ld();
+                    if (K < 7) tmem_ldw16(t_oth + 16 * (K + 1), obuf[(K + 1) & 1]);
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr)
+                        o[rr] = cplx_from_words(obuf[K & 1][4 * rr], obuf[K & 1][4 * rr + 1], obuf[K & 1][4 * rr + 2], obuf[K & 1][4 * rr + 3]);
+                } else {
+                    tmem_ld4(t_oth + 16 * K, o);
+                }
 #pragma unroll
                 for (int rr = 0; rr < 4; ++rr) go[rr] = g[(((K & 3) * 4 + rr) * 4 + g_oth) * 32];
                 mac_oth<K * 4>(X, o, go);
@@ -520,6 +544,37 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
         };
         auto do_tail = [&]() {
             // twist constants and own-index pairs from tensor memory; results to shared memory (rotated reads) and back
+            if constexpr (MODE == 2) {
+                // groups of 4 positions, the loads of group q + 1 in flight while group q is twisted, rounded and accumulated
+                uint32_t tb[2][16], ab[2][8];
+                tmem_ldw16(t_tw, tb[0]);
+                tmem_ldw8(t_acc, ab[0]);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    uint32_t (&tw)[16] = tb[q & 1];
+                    uint32_t (&w)[8] = ab[q & 1];
+                    tmem_wait_ld();
+                    if (q < 7) { tmem_ldw16(t_tw + 16 * (q + 1), tb[(q + 1) & 1]); tmem_ldw8(t_acc + 8 * (q + 1), ab[(q + 1) & 1]); }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const cplx t = cplx_from_words(tw[4 * u], tw[4 * u + 1], tw[4 * u + 2], tw[4 * u + 3]);
+                        const cplx x = X[4 * q + u];
+                        const double re = fma(-x.y, t.y, x.x * t.x);
+                        const double im = fma(x.y, t.x, x.x * t.y);
+                        pair_t<AccT> O;
+                        // round(v) mod 2^32 through the conversion unit: one F2I.S64 (|v| is 2^57 rms, 2^63 is 60 sigma away)
+                        // instead of the four DADDs of to_torus32 - the same integer, and the FP64 pipe is what bounds this kernel
+                        O.x = w[2 * u] + (FSC_TX_F2I ? (uint32_t)(uint64_t)__double2ll_rn(re) : to_acc_scaled<AccT>(re));
+                        O.y = w[2 * u + 1] + (FSC_TX_F2I ? (uint32_t)(uint64_t)__double2ll_rn(im) : to_acc_scaled<AccT>(im));
+                        acc[lane + 32 * tail_j2(4 * q + u)] = O;
+                        w[2 * u] = O.x; w[2 * u + 1] = O.y;
+                    }
+                    tmem_stw8(t_acc + 8 * q, w);
+                }
+                tmem_wait_st();
+                __syncwarp();
+                return;
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 uint32_t tw[32], w[16];
@@ -537,15 +592,8 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     pair_t<AccT> O;
-                    if constexpr (MODE == 2 && FSC_TX_F2I) {
-                        // round(v) mod 2^32 through the conversion unit: one F2I.S64 (|v| is 2^57 rms, 2^63 is 60 sigma away)
-                        // instead of the four DADDs of to_torus32 - the same integer, and the FP64 pipe is what bounds this kernel
-                        O.x = w[2 * u] + (uint32_t)(uint64_t)__double2ll_rn(re[u]);
-                        O.y = w[2 * u + 1] + (uint32_t)(uint64_t)__double2ll_rn(im[u]);
-                    } else {
-                        O.x = w[2 * u] + to_acc_scaled<AccT>(re[u]);
-                        O.y = w[2 * u + 1] + to_acc_scaled<AccT>(im[u]);
-                    }
+                    O.x = w[2 * u] + to_acc_scaled<AccT>(re[u]);
+                    O.y = w[2 * u + 1] + to_acc_scaled<AccT>(im[u]);
                     acc[lane + 32 * tail_j2(8 * k + u)] = O;
                     w[2 * u] = O.x; w[2 * u + 1] = O.y;
                 }
@@ -663,13 +711,14 @@ static void launch_pbs_stream_t(const void* bsk_f, const uint64_t* in_small, int
 static void launch_pbs_stream_tx(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
                                  const uint32_t* lut_idx, const OutDest& out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     static const int mode = [] { const char* e = getenv("FSC_STREAM_TX"); return e ? atoi(e) : 2; }();      // 0 / 1: comparison forms
-#define FSC_TX(MODE) do { \
-    const size_t smem = (MODE == 2 ? (size_t)4 * 2 * 32 * 33 * sizeof(cplx) \
+#define FSC_TX(...) do { \
+    const size_t smem = (mode == 2 ? (size_t)4 * 2 * 32 * 33 * sizeof(cplx) \
                                    : (size_t)4 * 2 * 1024 * sizeof(pair_t<uint32_t>) + (size_t)4 * 2 * kXBufDoubles * sizeof(double)) + \
                         (size_t)2 * kHalfCplx * sizeof(cplx) + (size_t)kTabTwist * sizeof(cplx) + 2 * 2 * sizeof(uint64_t) + 16; \
-    ensure_dynamic_smem(reinterpret_cast<const void*>(&pbs_stream_tx_kernel<MODE>), smem); \
-    pbs_stream_tx_kernel<MODE><<<(count + 3) / 4, 256, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts, lut_idx, \
-                                                                   out_big, out_idx, count, stream_tables<uint32_t>()); } while (0)
+    ensure_dynamic_smem(reinterpret_cast<const void*>(&pbs_stream_tx_kernel<__VA_ARGS__>), smem); \
+    pbs_stream_tx_kernel<__VA_ARGS__><<<(count + 3) / 4, 256, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts, lut_idx, \
+                                                                   out_big, out_idx, count, stream_tables<uint32_t>(), stagger); } while (0)
+    static const int stagger = [] { const char* e = getenv("FSC_TX_STAGGER"); return e ? atoi(e) : 0; }();
     if (mode) stream_uniform_constants_init();
     if (mode == 2) FSC_TX(2); else if (mode == 1) FSC_TX(1); else FSC_TX(0);
 #undef FSC_TX

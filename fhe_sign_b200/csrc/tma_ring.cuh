@@ -171,6 +171,10 @@ __device__ __forceinline__ void tmem_stw16(uint32_t taddr, const uint32_t (&w)[1
                  ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]),
                  "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]) : "memory");
 }
+__device__ __forceinline__ void tmem_stw8(uint32_t taddr, const uint32_t (&w)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
 __device__ __forceinline__ cplx cplx_from_words(uint32_t xl, uint32_t xh, uint32_t yl, uint32_t yh) {
     cplx c;
     c.x = __hiloint2double((int)xh, (int)xl);
