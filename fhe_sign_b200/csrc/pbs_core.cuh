@@ -256,6 +256,12 @@ FSC_HD uint64_t to_torus64(double v) {
 #endif
 }
 FSC_HD uint32_t to_torus32(double v) {   // v already divided by 2^32
+#if defined(__CUDA_ARCH__) && !defined(FSC_TORUS32_DADD)
+    // round(v) mod 2^32 through the conversion unit (one F2I.S64.F64, a unit the blind rotation leaves idle) instead of four
+    // DADDs on the FP64 pipe that bounds it: the same integer as the magic-number form below for |v| < 2^63 (|v| is 2^57 rms
+    // here - 2048 x 2 digits of 2^22 times 64-bit key words, scaled by 2^-32 -, 2^63 is 60 sigma away)
+    return (uint32_t)(uint64_t)__double2ll_rn(v);
+#endif
     const double big = 29014219670751100192948224.0;               // 1.5 * 2^84
     const double magic = 6755399441055744.0;                       // 1.5 * 2^52
     const double r = (v + big) - big;                              // nearest multiple of 2^32

@@ -52,6 +52,7 @@ FSC_HD void split_level1(int h, const LD& ld, const SP& sp, cplx (&w)[16]) {
     }
 }
 // levels 2..5 on the 16 slots of half h
+template <class SP> FSC_HD void split_levels35(int h, const SP& sp, cplx (&w)[16]);
 template <class SP>
 FSC_HD void split_levels25(int h, const SP& sp, cplx (&w)[16]) {
     {   // level 2: node m = h, constant entry 1, the odd node (h = 1) multiplies by i s
@@ -76,6 +77,10 @@ FSC_HD void split_levels25(int h, const SP& sp, cplx (&w)[16]) {
             }
         }
     }
+    split_levels35(h, sp, w);
+}
+template <class SP>
+FSC_HD void split_levels35(int h, const SP& sp, cplx (&w)[16]) {
 #pragma unroll
     for (int L = 3; L <= 5; ++L) {
         const int half = 16 >> (L - 1);
@@ -100,6 +105,56 @@ FSC_HD void split_levels25(int h, const SP& sp, cplx (&w)[16]) {
             }
         }
     }
+}
+
+// ---- the two UNIFORM passes (pass 0: g = 32, pass 2: g = 0) with the root parameter at compile time ---------------------
+// (the structure pass32_uniform exploits in pbs_core2.cuh, restricted to what does not depend on the half index h)
+//   G = 32: the level-1 constant is exp(i pi / 4) = c (1 + i): s hi = c (hi.x - hi.y, hi.x + hi.y), 4 instructions per output;
+//   G = 0 : the level-1 constant is 1 (2 instructions per output) and so is the level-2 constant (the odd node is i): four
+//           additions per butterfly.
+template <int G, class LD, class SP>
+FSC_HD void split_level1_u(int h, const LD& ld, const SP& sp, cplx (&w)[16]) {
+    static_assert(G == 0 || G == 32, "uniform tables only");
+    const double sg = h ? -1.0 : 1.0;
+    const double sgc = sg * sp.get(0).x;      // G = 32: +- cos(pi / 4)
+#pragma unroll
+    for (int j0 = 0; j0 < 16; j0 += 8) {
+        cplx lo[8], hi[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { lo[u] = ld(j0 + u); hi[u] = ld(16 + j0 + u); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (G == 0) {
+                w[j0 + u].x = fma(sg, hi[u].x, lo[u].x);
+                w[j0 + u].y = fma(sg, hi[u].y, lo[u].y);
+            } else {
+                const double qx = hi[u].x - hi[u].y, qy = hi[u].x + hi[u].y;
+                w[j0 + u].x = fma(sgc, qx, lo[u].x);
+                w[j0 + u].y = fma(sgc, qy, lo[u].y);
+            }
+        }
+    }
+}
+template <class SP> FSC_HD void split_levels35(int h, const SP& sp, cplx (&w)[16]);
+template <int G, class SP>
+FSC_HD void split_levels25_u(int h, const SP& sp, cplx (&w)[16]) {
+    if (G != 0) { split_levels25(h, sp, w); return; }
+    if (!h) {      // level 2, constant 1
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const cplx lo = w[j], hi = w[8 + j];
+            w[j].x = lo.x + hi.x;     w[j].y = lo.y + hi.y;
+            w[8 + j].x = lo.x - hi.x; w[8 + j].y = lo.y - hi.y;
+        }
+    } else {       // the odd node: constant i
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const cplx lo = w[j], hi = w[8 + j];
+            w[j].x = lo.x - hi.y;     w[j].y = lo.y + hi.x;
+            w[8 + j].x = lo.x + hi.y; w[8 + j].y = lo.y - hi.x;
+        }
+    }
+    split_levels35(h, sp, w);
 }
 
 template <class LD, class SP>
@@ -190,7 +245,8 @@ struct SplitLoadProduct {
 // hands the other one (same local index, other half) to its partner through X[h][j - 8 h][lane]; after a barrier
 // of the polynomial's two warps split_product_recv completes w with the partner's eight outputs.
 constexpr int kSplitXCplx = 2 * 8 * 32;          // exchange area of one polynomial, 8 KiB
-template <class SP>
+// UNIT: the level-1 constant of inverse pass A is 1 (g = 0): the butterfly is lo +- hi
+template <bool UNIT = false, class SP>
 FSC_HD void split_product_send(int lane, int h, const SplitLoadProduct& ld, const SP& sp, cplx* X, cplx (&w)[16]) {
     const cplx s = sp.get(0);
     constexpr int B = 4;                      // slot pairs per batch: 8 B loads in flight ahead of the arithmetic
@@ -203,8 +259,8 @@ FSC_HD void split_product_send(int lane, int h, const SplitLoadProduct& ld, cons
 #pragma unroll
             for (int u = 0; u < B; ++u) {
                 const cplx lo = SplitLoadProduct::mul(a[u]), hi = SplitLoadProduct::mul(b[u]);
-                const double tx = fma(-s.y, hi.y, s.x * hi.x);
-                const double ty = fma(s.y, hi.x, s.x * hi.y);
+                const double tx = UNIT ? hi.x : fma(-s.y, hi.y, s.x * hi.x);
+                const double ty = UNIT ? hi.y : fma(s.y, hi.x, s.x * hi.y);
                 w[j0 + u].x = lo.x + tx; w[j0 + u].y = lo.y + ty;
                 cplx o; o.x = lo.x - tx; o.y = lo.y - ty;
                 X[(j0 + u) * 32 + lane] = o;
@@ -219,8 +275,8 @@ FSC_HD void split_product_send(int lane, int h, const SplitLoadProduct& ld, cons
 #pragma unroll
             for (int u = 0; u < B; ++u) {
                 const cplx lo = SplitLoadProduct::mul(a[u]), hi = SplitLoadProduct::mul(b[u]);
-                const double tx = fma(-s.y, hi.y, s.x * hi.x);
-                const double ty = fma(s.y, hi.x, s.x * hi.y);
+                const double tx = UNIT ? hi.x : fma(-s.y, hi.y, s.x * hi.x);
+                const double ty = UNIT ? hi.y : fma(s.y, hi.x, s.x * hi.y);
                 w[8 + j0 + u].x = lo.x - tx; w[8 + j0 + u].y = lo.y - ty;
                 cplx o; o.x = lo.x + tx; o.y = lo.y + ty;
                 X[(8 + j0 + u) * 32 + lane] = o;

@@ -45,8 +45,13 @@ __device__ __forceinline__ void stream_head_u32(int lane, const pair_t<uint32_t>
         const int py = (int)(P.x + P.y) - px;
         const int dx = imad(px, sx, half - (int)O.x);
         const int dy = imad(py, sy, half - (int)O.y);
+#ifndef FSC_HEAD_MANTISSA      // int -> double through the conversion unit (A/B in one call, profiles/r02s_*: narrow levels -1.5 %, 149-296 blocks -5 %); FSC_HEAD_MANTISSA: the mantissa trick
+        z[j2].x = (double)(dx >> sh);
+        z[j2].y = (double)(dy >> sh);
+#else
         z[j2].x = __hiloint2double(0x43300000, (dx >> sh) ^ (int)0x80000000) - 4503601774854144.0;
         z[j2].y = __hiloint2double(0x43300000, (dy >> sh) ^ (int)0x80000000) - 4503601774854144.0;
+#endif
         // compiler-only ordering point every 4 elements: the four results must exist here, so the integer halves of
         // later elements cannot all be computed (and spilled) before the first conversion
         if ((j2 & 3) == 3) {

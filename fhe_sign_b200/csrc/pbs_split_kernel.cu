@@ -65,8 +65,13 @@ __device__ __forceinline__ void split_head_u32(int lane, int h, const pair_t<uin
         const int dx = imad(px, sx, half - (int)O.x);
         const int dy = imad(py, sy, half - (int)O.y);
         cplx z;
+#ifndef FSC_HEAD_MANTISSA      // int -> double through the conversion unit (see pbs_head.cuh)
+        z.x = (double)(dx >> sh);
+        z.y = (double)(dy >> sh);
+#else
         z.x = __hiloint2double(0x43300000, (dx >> sh) ^ (int)0x80000000) - 4503601774854144.0;
         z.y = __hiloint2double(0x43300000, (dy >> sh) ^ (int)0x80000000) - 4503601774854144.0;
+#endif
         e[jj * 32] = z;
     }
 }
@@ -75,6 +80,11 @@ __device__ __forceinline__ void split_head_dev(int lane, int h, const pair_t<Acc
     if constexpr (sizeof(AccT) == 4) split_head_u32(lane, h, poly, a, base_log, E);
     else split_head<AccT>(lane, h, poly, a, base_log, E);
 }
+#ifdef FSC_SPLIT_GENERIC      // comparison build: every pass through the generic routines
+constexpr bool kSplitUniform = false;
+#else
+constexpr bool kSplitUniform = true;
+#endif
 __device__ __forceinline__ void poly_barrier(int p) {      // the two warps of one polynomial
     if (p) asm volatile("bar.sync 2, 64;" ::: "memory");
     else asm volatile("bar.sync 1, 64;" ::: "memory");
@@ -200,7 +210,12 @@ __global__ void __launch_bounds__(128, 1) pbs_split_kernel(const cplx* __restric
         split_head_dev<AccT>(lane, h, acc, a, base_log, E);
         poly_barrier(p);
         FSC_POLL();
-        split_pass(h, SplitLoadE{E + lane}, c0, w);
+        if constexpr (PX == 1 && kSplitUniform) {      // uniform pass, root parameter at compile time (pbs_core3.cuh split_level1_u)
+            split_level1_u<32>(h, SplitLoadE{E + lane}, c0, w);
+            split_levels25(h, c0, w);
+        } else {
+            split_pass(h, SplitLoadE{E + lane}, c0, w);
+        }
         split_xp_store(lane, h, T, w);
         poly_barrier(p);
         split_pass(h, SplitLoadT{T + lane * kSplitTRow}, c1, w);
@@ -223,12 +238,12 @@ __global__ void __launch_bounds__(128, 1) pbs_split_kernel(const cplx* __restric
                                       ring + (size_t)st1 * kHalfCplx + lane, 3 * p, 2 - p};
             if constexpr (PX == 1) {
                 cplx* X = X_all + (size_t)p * kSplitXCplx;
-                split_product_send(lane, h, ld, c2, X, w);
+                split_product_send<kSplitUniform>(lane, h, ld, c2, X, w);      // g = 0: the level-1 constant is 1
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(empty + st0); mbar_arrive(empty + st1); }
                 poly_barrier(p);
                 split_product_recv(lane, h, X, w);
-                split_levels25(h, c2, w);
+                split_levels25_u<kSplitUniform ? 0 : 32>(h, c2, w);        // ... and so is the level-2 constant
             } else {
                 split_pass(h, ld, c2, w);
                 __syncwarp();

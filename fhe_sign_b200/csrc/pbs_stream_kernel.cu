@@ -235,6 +235,8 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_stream_kernel(const cplx* __r
         for (int q = 0; q < 4; ++q) {
             if (q == 0) do_head();
             else if (q & 1) xp_in(q == 1 ? lane : row_inv);
+            // (pass32_uniform for q = 0, 2 inside this rolled loop was measured: 5.10 -> 6.02 ms per 296 blocks - three pass bodies
+            // behind a switch, 255 registers and spills; the specialisation pays in the straight-line pbs_stream_tx_kernel<2> only)
             pass32(X, pass_table(tabs, q, lane));
             if (!(q & 1)) xp_out(q == 2);
             else if (q == 1) do_mac();
@@ -374,9 +376,11 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
     int stage = 0;
     uint32_t phase = 0;
     cplx X[32];
-    if (stagger > 0) {      // experiment (FSC_TX_STAGGER): ciphertext k of the CTA starts k * stagger cycles late
+    if (stagger != 0) {      // experiment (FSC_TX_STAGGER): ciphertexts of a CTA start at different times
         const long long t0 = clock64();
-        while (clock64() - t0 < (long long)stagger * ctl) { }
+        // stagger > 0: ciphertext k waits k * stagger; stagger < 0: two groups (ciphertexts 0, 1 | 2, 3), the second -stagger late
+        const long long wait = stagger > 0 ? (long long)stagger * ctl : (long long)(-stagger) * (ctl >> 1);
+        while (clock64() - t0 < wait) { }
         __syncwarp();
     }
     for (int i = 0; i < n; ++i) {

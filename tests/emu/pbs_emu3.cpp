@@ -37,7 +37,12 @@ void blind_rotate(int px, int n, int base_log, const cplx* bsk_f, const uint64_t
         const int a = modswitch(ct[i]);
         ALL split_head<AccT>(l, h, acc.data() + p * 1024, a, base_log, E.data() + p * kSplitECplx);
         // barrier
-        ALL split_pass(h, SplitLoadS{E.data() + p * kSplitECplx + l, 32}, StridedConsts{&T.t[0][0][l], 32}, w[p][h][l]);
+        if (px == 1) {      // the kernel's default form: uniform passes with the root parameter at compile time
+            ALL { split_level1_u<32>(h, SplitLoadS{E.data() + p * kSplitECplx + l, 32}, StridedConsts{&T.t[0][0][l], 32}, w[p][h][l]);
+                  split_levels25(h, StridedConsts{&T.t[0][0][l], 32}, w[p][h][l]); }
+        } else {
+            ALL split_pass(h, SplitLoadS{E.data() + p * kSplitECplx + l, 32}, StridedConsts{&T.t[0][0][l], 32}, w[p][h][l]);
+        }
         ALL split_xp_store(l, h, Tb.data() + p * kSplitTCplx, w[p][h][l]);
         // barrier
         ALL split_pass(h, SplitLoadT{Tb.data() + p * kSplitTCplx + l * kSplitTRow}, StridedConsts{&T.t[1][0][l], 32}, w[p][h][l]);
@@ -62,12 +67,12 @@ void blind_rotate(int px, int n, int base_log, const cplx* bsk_f, const uint64_t
         } else {        // product split between the two warps, level-1 outputs of the other half exchanged
             ALL {
                 SplitLoadProduct ld{E.data() + p * kSplitECplx + l, E.data() + (1 - p) * kSplitECplx + l, g + l, g + 16 * 4 * 32 + l, 3 * p, 2 - p};
-                split_product_send(l, h, ld, StridedConsts{&T.t[2][0][l], 32}, X.data() + p * kSplitXCplx, w[p][h][l]);
+                split_product_send<true>(l, h, ld, StridedConsts{&T.t[2][0][l], 32}, X.data() + p * kSplitXCplx, w[p][h][l]);
             }
             // barrier
             ALL {
                 split_product_recv(l, h, X.data() + p * kSplitXCplx, w[p][h][l]);
-                split_levels25(h, StridedConsts{&T.t[2][0][l], 32}, w[p][h][l]);
+                split_levels25_u<0>(h, StridedConsts{&T.t[2][0][l], 32}, w[p][h][l]);
             }
         }
         ALL split_xp_store(l, h, Tb.data() + p * kSplitTCplx, w[p][h][l]);
