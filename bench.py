@@ -45,8 +45,8 @@ FP64_NOMINAL_TF = 148 * 64 * 2 * 1.965e9 / 1e12      # 148 SMs x 6
 
 
 # DRAM bytes (read + write) of one 4096-block launch, from the committed ncu --set full captures (NOT measured in this run)
-NCU_TRAFFIC = {"pbs_ring_kernel": 202.69e6, "pbs_stream_kernel": 233.47e6}
-NCU_TRAFFIC_SOURCE = "profiles/r01c_ncu_key_metrics.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch; constant, not re-measured here)"
+NCU_TRAFFIC = {"pbs_ring_kernel": 202.69e6, "pbs_stream_kernel": 233.47e6, "pbs_stream_tx_kernel": 261.73e6}
+NCU_TRAFFIC_SOURCE = "profiles/r02s_ncu_key_metrics.json / r01c_ncu_key_metrics.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch; constant, not re-measured here)"
 
 
 def flops_per_pbs(n, N=2048, k=1, l=1):
