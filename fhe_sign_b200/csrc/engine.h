@@ -43,6 +43,7 @@ struct Engine {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<cudaEvent_t> chunk_events;
+    bool host_chunk_explicit = false;    // FSC_HOST_CHUNK_WAVES given: uniform chunks instead of the first-wave | middle | last-wave plan
     size_t host_chunk_waves = 1;         // chunk = this many waves of the blind-rotation kernel (FSC_HOST_CHUNK_WAVES; 0 = no overlap)
 
     Engine(const fsc_params& prm, int device, uintptr_t ext_stream);

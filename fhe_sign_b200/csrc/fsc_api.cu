@@ -75,7 +75,7 @@ Engine::Engine(const fsc_params& prm, int device, uintptr_t ext_stream) : p(prm)
     ks_variant = (kv && kv[0] == 's') ? 0 : (kv && kv[0] == 'm') ? 1 : 2;      // simt | mma | umma (default)
     if (const char* wk = getenv("FSC_PBS_WIDE")) wide_tx = wk[0] != 'r';         // "ring": wide batches stay on the ring kernel (comparison)
     if (const char* ns = getenv("FSC_PBS_SPLIT")) use_split = atoi(ns) != 0;      // 0: narrow levels stay on the stream kernel
-    if (const char* hw = getenv("FSC_HOST_CHUNK_WAVES")) host_chunk_waves = (size_t)atoi(hw);      // 0: one chunk, copies not overlapped
+    if (const char* hw = getenv("FSC_HOST_CHUNK_WAVES")) { host_chunk_waves = (size_t)atoi(hw); host_chunk_explicit = true; }      // 0: one chunk, copies not overlapped
 }
 
 void Engine::ensure_copy_streams() {
@@ -562,10 +562,25 @@ fsc_status fsc_apply_lut_host(fsc_ctx* ctx, const uint64_t* in_host, const fsc_l
             FSC_CUDA_CHECK(cudaEventRecord(e->ev_fork, e->stream));          // staging buffers are free once earlier work is done
             FSC_CUDA_CHECK(cudaStreamWaitEvent(e->copy_in, e->ev_fork, 0));
             FSC_CUDA_CHECK(cudaStreamWaitEvent(e->copy_out, e->ev_fork, 0));
+            // chunk plan.  Default: first wave | everything between, as ONE launch | last (partial) wave — every launch boundary is a
+            // barrier of the whole GPU on the slowest SM of the wave before it (7 one-wave launches of a 4096-block batch cost 2.8 ms
+            // against 3 launches), while the uploads stream back to back and only the first upload (one wave) and the last download
+            // stay exposed.  FSC_HOST_CHUNK_WAVES=k: uniform chunks of k waves (comparison).
+            std::vector<std::pair<size_t, size_t>> plan;
+            if (!e->host_chunk_explicit && count > 2 * wave + wave / 2) {
+                size_t last = (count - wave) % wave;
+                if (last == 0) last = wave;
+                plan.emplace_back(0, wave);
+                plan.emplace_back(wave, count - wave - last);
+                plan.emplace_back(count - last, last);
+            } else {
+                for (size_t off = 0; off < count; off += chunk) plan.emplace_back(off, std::min(chunk, count - off));
+            }
             size_t k = 0;
-            for (size_t off = 0; off < count; off += chunk, ++k) {
-                const size_t c = std::min(chunk, count - off);
-                cudaEvent_t up = e->chunk_event(2 * k), done = e->chunk_event(2 * k + 1);
+            for (const auto& pc : plan) {
+                const size_t off = pc.first, c = pc.second;
+                ++k;
+                cudaEvent_t up = e->chunk_event(2 * (k - 1)), done = e->chunk_event(2 * (k - 1) + 1);
                 FSC_CUDA_CHECK(cudaMemcpyAsync(din + off * words, in_host + off * words, c * words * 8, cudaMemcpyHostToDevice, e->copy_in));
                 FSC_CUDA_CHECK(cudaEventRecord(up, e->copy_in));
                 FSC_CUDA_CHECK(cudaStreamWaitEvent(e->stream, up, 0));
