@@ -52,6 +52,10 @@ Engine::Engine(const fsc_params& prm, int device, uintptr_t ext_stream) : p(prm)
     if (pbs_variant_for((int)p.acc_bits) >= 5 && p.acc_bits != 32) throw Error(FSC_ERR_PARAMS, "the solo and quad kernels exist for the 32-bit accumulator only");
     if (p.lwe_dim == 0 || p.lwe_dim > 4096 || p.pbs_base_log < 8 || p.pbs_base_log > 30)
         throw Error(FSC_ERR_PARAMS, "lwe_dim / pbs_base_log out of range");
+    // The 32-bit accumulator kernels round through F2I.S64.F64 (pbs_core.cuh to_torus32): the value being rounded is
+    // 2^(pbs_base_log + 34.4) rms, so base_log 24 leaves 2^63 at 24 sigma; beyond that the conversion could saturate.
+    if (p.acc_bits == 32 && p.pbs_base_log > 24)
+        throw Error(FSC_ERR_PARAMS, "acc_bits = 32 supports pbs_base_log <= 24 (use the 64-bit accumulator above that)");
     if (p.ks_level == 0 || p.ks_level > 8 || p.ks_base_log == 0 || p.ks_base_log > 7)
         throw Error(FSC_ERR_PARAMS, "keyswitch decomposition out of range");
     if (p.message_modulus * p.carry_modulus == 0 || (p.poly_size % (p.message_modulus * p.carry_modulus)) != 0)

@@ -56,7 +56,8 @@ typedef struct {
     uint32_t message_modulus;  /* 4                                                   */
     uint32_t carry_modulus;    /* 4                                                   */
     uint32_t acc_bits;         /* blind-rotation accumulator width: 32 (default if 0: adds variance 2^-60 to a PBS
-                                * variance of 2^-30, measured sigma identical, 1.5x the throughput) or 64    */
+                                * variance of 2^-30, measured sigma identical, 1.9x the throughput; needs
+                                * pbs_base_log <= 24: its kernels round through F2I.S64) or 64               */
 } fsc_params;
 
 typedef struct fsc_ctx fsc_ctx;          /* replaces the thread-local tfhe ServerKey              */

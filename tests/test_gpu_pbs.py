@@ -198,6 +198,12 @@ def test_error_codes(gpu_ctx, oracle_keys):
         fsb.Context(fsb.Params.preset("toy").__class__(lwe_dim=48, glwe_dim=2, poly_size=1024, pbs_base_log=23, pbs_level=1,
                                                        ks_base_log=3, ks_level=5, message_modulus=4, carry_modulus=4, acc_bits=64))
     assert ei.value.code == 2
+    # the 32-bit accumulator rounds through F2I.S64 (|v| ~ 2^(base_log + 34.4) rms): base_log > 24 is refused there, accepted at 64 bits
+    wide = dict(lwe_dim=48, glwe_dim=1, poly_size=2048, pbs_base_log=26, pbs_level=1, ks_base_log=3, ks_level=5, message_modulus=4, carry_modulus=4)
+    with pytest.raises(fsb.FscError) as ei:
+        fsb.Context(fsb.Params.preset("toy").__class__(acc_bits=32, **wide))
+    assert ei.value.code == 2
+    fsb.Context(fsb.Params.preset("toy").__class__(acc_bits=64, **wide)).close()
     ctx.close()
 
 
