@@ -49,7 +49,7 @@ Engine::Engine(const fsc_params& prm, int device, uintptr_t ext_stream) : p(prm)
     if (p.glwe_dim != 1 || p.poly_size != 2048 || p.pbs_level != 1)
         throw Error(FSC_ERR_PARAMS, "kernels are specialised for glwe_dim=1, poly_size=2048, pbs_level=1");
     if (p.acc_bits != 64 && p.acc_bits != 32) throw Error(FSC_ERR_PARAMS, "acc_bits must be 32 or 64");
-    if (pbs_variant_for((int)p.acc_bits) >= 5 && p.acc_bits != 32) throw Error(FSC_ERR_PARAMS, "the solo and quad kernels exist for the 32-bit accumulator only");
+    if (pbs_variant_for((int)p.acc_bits) >= 5 && p.acc_bits != 32) throw Error(FSC_ERR_PARAMS, "the solo, quad and duo kernels exist for the 32-bit accumulator only");
     if (p.lwe_dim == 0 || p.lwe_dim > 4096 || p.pbs_base_log < 8 || p.pbs_base_log > 30)
         throw Error(FSC_ERR_PARAMS, "lwe_dim / pbs_base_log out of range");
     // The 32-bit accumulator kernels round through F2I.S64.F64 (pbs_core.cuh to_torus32): the value being rounded is
@@ -164,7 +164,7 @@ void Engine::upload_keys(const uint64_t* bsk_std, size_t bsk_words, const uint64
     // Fourier key: correctly rounded direct DFT in double-double arithmetic (bsk_exact.cu: removes the key's share of the
     // floating-point noise, measured 7-11 % of the output variance); FSC_BSK_CONVERT=fft keeps the kernels' own f64 FFT
     // (comparison).  Layouts: ring order for the ring / pair kernels, stream order for the stream / split / solo kernels.
-    const bool stream_main = variant == 2 || variant == 4, both = variant == 3 || variant == 5 || variant == 6;
+    const bool stream_main = variant == 2 || variant == 4, both = variant == 3 || variant == 5 || variant == 6 || variant == 7;
     if (both) ns.alloc(fourier_bytes);
     const char* conv = getenv("FSC_BSK_CONVERT");
     if (conv && conv[0] == 'f') {
@@ -270,7 +270,7 @@ void Engine::pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut
     const OutDest od = dests ? *dests : single_dest(out_big);
     // variant 3: levels of at most one ciphertext per SM on the split kernel (four warps per ciphertext: the latency-bound
     // case), up to two per SM on the stream kernel, wide batches on the ring kernel
-    const bool mixed = pbs_variant == 3 || pbs_variant == 5 || pbs_variant == 6;      // narrow levels on the split / stream kernels, wide ones on ring (3), solo (5) or quad (6)
+    const bool mixed = pbs_variant == 3 || pbs_variant == 5 || pbs_variant == 6 || pbs_variant == 7;      // narrow levels on the split / stream kernels, wide ones on ring (3), solo (5) or quad (6)
     if (pbs_variant == 4 || (mixed && use_split && (int)count <= sm_count))
         launch_pbs_split((int)p.acc_bits, pbs_variant == 4 ? bsk_f : bsk_s, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d,
                          lut_idx_dev, od, out_idx_dev, (int)count, stream);
@@ -279,6 +279,8 @@ void Engine::pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut
                           out_idx_dev, (int)count, sm_count, stream);
     else if (pbs_variant == 5)
         launch_pbs_solo(bsk_s, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, od, out_idx_dev, (int)count, stream);
+    else if (pbs_variant == 7)
+        launch_pbs_duo(bsk_s, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, od, out_idx_dev, (int)count, stream);
     else if (pbs_variant == 6)
         launch_pbs_quad(bsk_s, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, od, out_idx_dev, (int)count, stream);
     else if (pbs_variant == 2)
@@ -629,7 +631,7 @@ const char* fsc_pbs_kernel_name(const fsc_ctx* ctx) {
     if (!ctx) return "";
     const int v = ctx->eng->bsk_f ? ctx->eng->pbs_variant : fsc::pbs_variant_for((int)ctx->eng->p.acc_bits);
     if (v == 3 && ctx->eng->p.acc_bits == 32 && ctx->eng->wide_tx) return "pbs_stream_tx_kernel";
-    return v == 6 ? "pbs_quad_kernel" : v == 5 ? "pbs_solo_kernel" : v == 4 ? "pbs_split_kernel" : v == 2 ? "pbs_stream_kernel" : v == 0 ? "pbs_pair_kernel" : "pbs_ring_kernel";
+    return v == 7 ? "pbs_duo_kernel" : v == 6 ? "pbs_quad_kernel" : v == 5 ? "pbs_solo_kernel" : v == 4 ? "pbs_split_kernel" : v == 2 ? "pbs_stream_kernel" : v == 0 ? "pbs_pair_kernel" : "pbs_ring_kernel";
 }
 
 fsc_status fsc_measure_fp64_peak(fsc_ctx* ctx, double* tflops) {

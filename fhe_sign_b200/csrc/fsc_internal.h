@@ -81,7 +81,10 @@ void launch_negacyclic_mul_stream(const uint64_t* a, const int64_t* b, uint64_t*
 // pbs_quad_kernel.cu (wide batches, four warps per ciphertext at 128 registers, sibling exchange through tensor memory; the stream kernel's key layout; 32-bit accumulator)
 void launch_pbs_quad(const void* bsk_fourier, const uint64_t* in_small, int n, int base_log, const uint64_t* luts, const uint32_t* lut_idx,
                      const OutDest& out_big, const int32_t* out_idx, int count, cudaStream_t st);
-// 0: pair, 1: ring, 2: stream, 3: ring (wide) + stream / split (narrow), 4: split, 5: solo (wide) + stream / split (narrow), 6: quad (wide) + stream / split (narrow)
+// pbs_duo_kernel.cu (wide batches, two warps per ciphertext, each carrying half of BOTH polynomials as two instruction streams one segment apart; 32-bit accumulator)
+void launch_pbs_duo(const void* bsk_fourier, const uint64_t* in_small, int n, int base_log, const uint64_t* luts, const uint32_t* lut_idx,
+                    const OutDest& out_big, const int32_t* out_idx, int count, cudaStream_t st);
+// 7: duo (wide) + stream / split (narrow);  0: pair, 1: ring, 2: stream, 3: ring (wide) + stream / split (narrow), 4: split, 5: solo (wide) + stream / split (narrow), 6: quad (wide) + stream / split (narrow)
 // (FSC_PBS_VARIANT, else by accumulator width);
 // fixed per context at key upload
 int pbs_variant_for(int acc_bits);

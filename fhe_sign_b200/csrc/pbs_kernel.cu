@@ -691,7 +691,8 @@ int pbs_variant_for(int acc_bits) {
     if (e && e[0] == 's' && e[1] == 'p') return 4;      // "split": the latency kernel at every width (tests)
     if (e && e[0] == 's' && e[1] == 'o') return 5;      // "solo": one warp per ciphertext for wide batches, split / stream below
     if (e && e[0] == 's') return 2;
-    if (e && e[0] == 'q') return 6;      // "quad": four warps per ciphertext at 128 registers for wide batches, split / stream below
+    if (e && e[0] == 'q') return 6;
+    if (e && e[0] == 'd') return 7;      // "duo": two instruction streams per warp for wide batches, split / stream below      // "quad": four warps per ciphertext at 128 registers for wide batches, split / stream below
     if (e && e[0] == 'a') return 3;
     return acc_bits == 32 ? 3 : 1;
 }

@@ -78,15 +78,15 @@ def test_pbs_all_messages_all_luts(gpu_ctx, oracle_keys, rng, preset, acc_bits):
 
 
 @pytest.mark.parametrize("acc_bits", [32, 64])
-@pytest.mark.parametrize("variant", ["auto", "stream", "ring", "pair", "split", "solo", "quad", "stream-tx0", "stream-tx1", "auto-ring"])
+@pytest.mark.parametrize("variant", ["auto", "stream", "ring", "pair", "split", "solo", "quad", "duo", "stream-tx0", "stream-tx1", "auto-ring"])
 def test_pbs_kernel_variants_all_widths(oracle_keys, orc, rng, variant, acc_bits, monkeypatch):
     """Every blind-rotation kernel (FSC_PBS_VARIANT) at batch widths that select each of its configurations
     (1, 2 and 3-4 ciphertexts per CTA, ragged last CTA): decrypted values equal the table, noise inside the budget.
     The Fourier key layout follows the variant, so this also checks both key conversions."""
     import fhe_sign_b200 as fsb
     from fhe_sign_b200.capi import LWE_BIG
-    if variant in ("solo", "quad", "stream-tx0", "stream-tx1") and acc_bits != 32:
-        pytest.skip("the solo, quad and tensor-memory stream kernels exist for the 32-bit accumulator only")
+    if variant in ("solo", "quad", "duo", "stream-tx0", "stream-tx1") and acc_bits != 32:
+        pytest.skip("the solo, quad, duo and tensor-memory stream kernels exist for the 32-bit accumulator only")
     if variant.startswith("stream-tx"):      # comparison forms of the wide-batch stream kernel (default: FSC_STREAM_TX=2)
         monkeypatch.setenv("FSC_STREAM_TX", variant[-1])
         variant = "stream"

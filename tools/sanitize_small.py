@@ -20,7 +20,7 @@ def main():
     K = orc.Keys(orc.preset("toy"), 1)
     table = (np.arange(16) * 5 + 2) % 16
     rng = np.random.default_rng(2)
-    for variant, acc_bits, counts in (("auto", 32, (5, 160, 310)), ("auto", 64, (5, 310)), ("solo", 32, (310,)), ("quad", 32, (310, 593))):
+    for variant, acc_bits, counts in (("auto", 32, (5, 160, 310)), ("auto", 64, (5, 310)), ("solo", 32, (310,)), ("quad", 32, (310, 593)), ("duo", 32, (310, 593))):
         os.environ["FSC_PBS_VARIANT"] = variant
         ctx = fsb.Context(fsb.Params.preset("toy", acc_bits=acc_bits))
         ctx.upload_keys(K.bsk, K.ksk)                      # bsk_exact_kernel, ksk_limb_transpose_kernel
@@ -28,7 +28,7 @@ def main():
         for count in counts:
             m = rng.integers(0, 16, count).astype(np.uint64)
             din, dout = ctx.lwe(LWE_BIG, count).upload(K.encrypt_msgs(m)), ctx.lwe(LWE_BIG, count)
-            ctx.ks_pbs(din, luts, None, dout)              # ks_decompose_kernel, ks_umma_kernel, pbs_{split,stream,ring,solo,quad}_kernel
+            ctx.ks_pbs(din, luts, None, dout)              # ks_decompose_kernel, ks_umma_kernel, pbs_{split,stream,ring,solo,quad,duo}_kernel
             ok = (K.decrypt_msgs(dout.download()) == table[m]).all()
             print("%s acc %d count %d kernel %s: %s" % (variant, acc_bits, count, ctx.pbs_kernel_name(), "ok" if ok else "WRONG"), flush=True)
             assert ok
