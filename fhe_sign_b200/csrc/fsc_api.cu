@@ -49,7 +49,7 @@ Engine::Engine(const fsc_params& prm, int device, uintptr_t ext_stream) : p(prm)
     if (p.glwe_dim != 1 || p.poly_size != 2048 || p.pbs_level != 1)
         throw Error(FSC_ERR_PARAMS, "kernels are specialised for glwe_dim=1, poly_size=2048, pbs_level=1");
     if (p.acc_bits != 64 && p.acc_bits != 32) throw Error(FSC_ERR_PARAMS, "acc_bits must be 32 or 64");
-    if (pbs_variant_for((int)p.acc_bits) >= 5 && p.acc_bits != 32) throw Error(FSC_ERR_PARAMS, "the solo, quad and duo kernels exist for the 32-bit accumulator only");
+    if (pbs_variant_for((int)p.acc_bits) >= 5 && pbs_variant_for((int)p.acc_bits) <= 7 && p.acc_bits != 32) throw Error(FSC_ERR_PARAMS, "the solo, quad and duo kernels exist for the 32-bit accumulator only");
     if (p.lwe_dim == 0 || p.lwe_dim > 4096 || p.pbs_base_log < 8 || p.pbs_base_log > 30)
         throw Error(FSC_ERR_PARAMS, "lwe_dim / pbs_base_log out of range");
     // The 32-bit accumulator kernels round through F2I.S64.F64 (pbs_core.cuh to_torus32): the value being rounded is
@@ -164,7 +164,7 @@ void Engine::upload_keys(const uint64_t* bsk_std, size_t bsk_words, const uint64
     // Fourier key: correctly rounded direct DFT in double-double arithmetic (bsk_exact.cu: removes the key's share of the
     // floating-point noise, measured 7-11 % of the output variance); FSC_BSK_CONVERT=fft keeps the kernels' own f64 FFT
     // (comparison).  Layouts: ring order for the ring / pair kernels, stream order for the stream / split / solo kernels.
-    const bool stream_main = variant == 2 || variant == 4, both = variant == 3 || variant == 5 || variant == 6 || variant == 7;
+    const bool stream_main = variant == 2 || variant == 4, both = variant == 3 || variant == 5 || variant == 6 || variant == 7 || variant == 8;
     if (both) ns.alloc(fourier_bytes);
     const char* conv = getenv("FSC_BSK_CONVERT");
     if (conv && conv[0] == 'f') {
@@ -291,8 +291,12 @@ void Engine::pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut
         // passes specialised (pbs_stream_tx_kernel<2>: 83.5 k PBS/s against 77.7 k for the ring kernel, profiles/README.md)
         launch_pbs_stream((int)p.acc_bits, bsk_s, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, od,
                           out_idx_dev, (int)count, sm_count, stream);
+    else if (pbs_variant == 8 && wide_tx && (int)count > 2 * sm_count)
+        // wide batches at the reference's accumulator width: the straight-line stream kernel with four ciphertexts per SM
+        launch_pbs_stream((int)p.acc_bits, bsk_s, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, od,
+                          out_idx_dev, (int)count, sm_count, stream);
     else
-        launch_pbs(pbs_variant, (int)p.acc_bits, bsk_f, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, od,
+        launch_pbs(pbs_variant == 8 ? 1 : pbs_variant, (int)p.acc_bits, bsk_f, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d, lut_idx_dev, od,
                    out_idx_dev, (int)count, sm_count, stream);
     ++launches;
     FSC_CUDA_CHECK(cudaGetLastError());
@@ -630,7 +634,7 @@ fsc_status fsc_launch_count(const fsc_ctx* ctx, uint64_t* out) {
 const char* fsc_pbs_kernel_name(const fsc_ctx* ctx) {
     if (!ctx) return "";
     const int v = ctx->eng->bsk_f ? ctx->eng->pbs_variant : fsc::pbs_variant_for((int)ctx->eng->p.acc_bits);
-    if (v == 3 && ctx->eng->p.acc_bits == 32 && ctx->eng->wide_tx) return "pbs_stream_tx_kernel";
+    if ((v == 3 && ctx->eng->p.acc_bits == 32 && ctx->eng->wide_tx) || (v == 8 && ctx->eng->wide_tx)) return "pbs_stream_tx_kernel";
     return v == 7 ? "pbs_duo_kernel" : v == 6 ? "pbs_quad_kernel" : v == 5 ? "pbs_solo_kernel" : v == 4 ? "pbs_split_kernel" : v == 2 ? "pbs_stream_kernel" : v == 0 ? "pbs_pair_kernel" : "pbs_ring_kernel";
 }
 

@@ -276,13 +276,19 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_stream_kernel(const cplx* __r
 #ifndef FSC_TX_ST
 #define FSC_TX_ST 2      // spectrum stores of MODE 2: 2 = one double per tcgen05.st, 4 = one complex, 16 = four complex (gathered)
 #endif
-template <int MODE>
+// AccT = uint64_t (MODE 2 only): the reference's accumulator width with the same four ciphertexts per SM.  The accumulator lives
+// in tensor memory (128 columns per warp at [256, 512): where the 32-bit form keeps its accumulator and the twist constants), the
+// by-index copy in the transpose buffer takes 16 KB of the 16.5 KB buffer and is complete whenever the head runs (the portable
+// cmux_head reads rotated and own pairs from it; the transposes destroy it afterwards, the tail rewrites it), and the twist
+// constants come from global memory (L2-resident table, requested one group ahead).
+template <int MODE, typename AccT = uint32_t>
 __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __restrict__ bsk_f, const uint64_t* __restrict__ in_small,
                                                                  int n, int base_log, const uint64_t* __restrict__ luts,
                                                                  const uint32_t* __restrict__ lut_idx, const __grid_constant__ OutDest out_big,
                                                                  const int32_t* __restrict__ out_idx, int count,
                                                                  const cplx* __restrict__ tabs_g, int stagger) {
-    typedef uint32_t AccT;
+    constexpr bool ACC64 = sizeof(AccT) == 8;
+    static_assert(!ACC64 || MODE == 2, "the 64-bit accumulator exists in the straight-line form only");
     constexpr int CTS = 4, NH = 2;
     constexpr int kTmAcc = 256, kTmTwist = 384, kTmemCols = 512;
     constexpr int kTabNoTwist = kTabTwist;               // the twist table lives in tensor memory
@@ -336,8 +342,10 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
     const uint32_t t_quarter = tmem_base + ((uint32_t)(ctl * 32) << 16);
     const uint32_t t_own = t_quarter + (uint32_t)(p * 128), t_oth = t_quarter + (uint32_t)((1 - p) * 128);
     const uint32_t t_acc = t_quarter + kTmAcc + (uint32_t)(p * 64), t_tw = t_quarter + kTmTwist;
+    const uint32_t t_acc64 = t_quarter + kTmAcc + (uint32_t)(p * 128);      // 64-bit accumulator: [position][x lo, x hi, y lo, y hi]
+    (void)t_acc64;
 
-    if (p == 0) {      // the lane's twist constants, position order: 8 x 16 columns
+    if (p == 0 && !ACC64) {      // the lane's twist constants, position order: 8 x 16 columns
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             cplx v4[4];
@@ -349,7 +357,22 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
             tmem_st4(t_tw + 16 * k, v4);
         }
     }
-    {   // accumulator <- (0, X^{-b} LUT): shared memory by index, tensor memory in the tail's position order
+    if constexpr (ACC64) {      // accumulator <- (0, X^{-b} LUT): by index in the warp's transpose buffer, position order in tensor memory
+        const int b = modswitch(ct[n]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            uint32_t w[16];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = lane + 32 * tail_j2(4 * q + u);
+                pair_t<AccT> z; z.x = 0; z.y = 0;
+                if (p) z = lut_pair<AccT>(lut, idx, b);
+                acc[idx] = z;
+                w[4 * u] = (uint32_t)z.x; w[4 * u + 1] = (uint32_t)(z.x >> 32); w[4 * u + 2] = (uint32_t)z.y; w[4 * u + 3] = (uint32_t)(z.y >> 32);
+            }
+            tmem_stw16(t_acc64 + 16 * q, w);
+        }
+    } else {   // accumulator <- (0, X^{-b} LUT): shared memory by index, tensor memory in the tail's position order
         const int b = modswitch(ct[n]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -388,6 +411,7 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
         const int a = __shfl_sync(0xffffffffu, a_chunk, i & 31);
 
         auto do_head = [&]() {
+            if constexpr (ACC64) { cmux_head<AccT>(lane, acc, a, base_log, X); return; }
             // stream_head_u32 with the own-index pairs from tensor memory; elements visited in the tail's position order
             const int sh = 32 - base_log;
             const int half = 1 << (sh - 1);
@@ -548,7 +572,39 @@ __global__ void __launch_bounds__(256, 1) pbs_stream_tx_kernel(const cplx* __res
         };
         auto do_tail = [&]() {
             // twist constants and own-index pairs from tensor memory; results to shared memory (rotated reads) and back
-            if constexpr (MODE == 2) {
+            if constexpr (ACC64) {
+                // groups of 4 positions: accumulator words from tensor memory and twist constants from global memory one group ahead
+                const double2* twg = reinterpret_cast<const double2*>(tabs_g + kTabTwist) + lane;
+                uint32_t ab[2][16];
+                double2 tg[2][4];
+                tmem_ldw16(t_acc64, ab[0]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) tg[0][u] = __ldg(twg + u * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    uint32_t (&w)[16] = ab[q & 1];
+                    tmem_wait_ld();
+                    if (q < 7) {
+                        tmem_ldw16(t_acc64 + 16 * (q + 1), ab[(q + 1) & 1]);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) tg[(q + 1) & 1][u] = __ldg(twg + (4 * (q + 1) + u) * 32);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double2 t = tg[q & 1][u];
+                        const cplx x = X[4 * q + u];
+                        pair_t<AccT> O;
+                        O.x = ((uint64_t)w[4 * u + 1] << 32 | w[4 * u]) + to_acc_scaled<AccT>(fma(-x.y, t.y, x.x * t.x));
+                        O.y = ((uint64_t)w[4 * u + 3] << 32 | w[4 * u + 2]) + to_acc_scaled<AccT>(fma(x.y, t.x, x.x * t.y));
+                        acc[lane + 32 * tail_j2(4 * q + u)] = O;
+                        w[4 * u] = (uint32_t)O.x; w[4 * u + 1] = (uint32_t)(O.x >> 32); w[4 * u + 2] = (uint32_t)O.y; w[4 * u + 3] = (uint32_t)(O.y >> 32);
+                    }
+                    tmem_stw16(t_acc64 + 16 * q, w);
+                }
+                tmem_wait_st();
+                __syncwarp();
+                return;
+            } else if constexpr (MODE == 2) {
                 // groups of 4 positions, the loads of group q + 1 in flight while group q is twisted, rounded and accumulated
                 uint32_t tb[2][16], ab[2][8];
                 tmem_ldw16(t_tw, tb[0]);
@@ -712,19 +768,21 @@ static void launch_pbs_stream_t(const void* bsk_f, const uint64_t* in_small, int
                                                                           lut_idx, out_big, out_idx, count, stream_tables<AccT>());
 }
 
+template <typename AccT>
 static void launch_pbs_stream_tx(const void* bsk_f, const uint64_t* in_small, int n, int base_log, const uint64_t* luts,
                                  const uint32_t* lut_idx, const OutDest& out_big, const int32_t* out_idx, int count, cudaStream_t st) {
     static const int mode = [] { const char* e = getenv("FSC_STREAM_TX"); return e ? atoi(e) : 2; }();      // 0 / 1: comparison forms
 #define FSC_TX(...) do { \
-    const size_t smem = (mode == 2 ? (size_t)4 * 2 * 32 * 33 * sizeof(cplx) \
+    const size_t smem = ((mode == 2 || sizeof(AccT) == 8) ? (size_t)4 * 2 * 32 * 33 * sizeof(cplx) \
                                    : (size_t)4 * 2 * 1024 * sizeof(pair_t<uint32_t>) + (size_t)4 * 2 * kXBufDoubles * sizeof(double)) + \
                         (size_t)2 * kHalfCplx * sizeof(cplx) + (size_t)kTabTwist * sizeof(cplx) + 2 * 2 * sizeof(uint64_t) + 16; \
     ensure_dynamic_smem(reinterpret_cast<const void*>(&pbs_stream_tx_kernel<__VA_ARGS__>), smem); \
     pbs_stream_tx_kernel<__VA_ARGS__><<<(count + 3) / 4, 256, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts, lut_idx, \
-                                                                   out_big, out_idx, count, stream_tables<uint32_t>(), stagger); } while (0)
+                                                                   out_big, out_idx, count, stream_tables<AccT>(), stagger); } while (0)
     static const int stagger = [] { const char* e = getenv("FSC_TX_STAGGER"); return e ? atoi(e) : 0; }();
-    if (mode) stream_uniform_constants_init();
-    if (mode == 2) FSC_TX(2); else if (mode == 1) FSC_TX(1); else FSC_TX(0);
+    if (mode || sizeof(AccT) == 8) stream_uniform_constants_init();
+    if constexpr (sizeof(AccT) == 8) { FSC_TX(2, uint64_t); }
+    else { if (mode == 2) FSC_TX(2); else if (mode == 1) FSC_TX(1); else FSC_TX(0); }
 #undef FSC_TX
 }
 
@@ -740,12 +798,13 @@ void launch_pbs_stream(int acc_bits, const void* bsk_f, const uint64_t* in_small
         if (count <= sm_count) FSC_STREAM(uint32_t, 1, 3);
         else if (count <= 2 * sm_count) FSC_STREAM(uint32_t, 2, 3);
         else if (getenv("FSC_STREAM_NO_TMEM")) FSC_STREAM(uint32_t, 4, 2);
-        else launch_pbs_stream_tx(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
+        else launch_pbs_stream_tx<uint32_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
     } else {
         // 64-bit accumulator: two ciphertexts per CTA is what fits beside a whole-step ring (the product default for
         // 64-bit accumulators is the ring kernel of pbs_kernel.cu, three per CTA)
         if (count <= sm_count) FSC_STREAM(uint64_t, 1, 3);
-        else FSC_STREAM(uint64_t, 2, 2);
+        else if (count <= 2 * sm_count || getenv("FSC_STREAM_NO_TMEM")) FSC_STREAM(uint64_t, 2, 2);
+        else launch_pbs_stream_tx<uint64_t>(bsk_f, in_small, n, base_log, luts, lut_idx, out_big, out_idx, count, st);
     }
 #undef FSC_STREAM
 }
