@@ -270,7 +270,7 @@ void Engine::pbs(const uint64_t* in_small, const Luts* luts, const uint32_t* lut
     const OutDest od = dests ? *dests : single_dest(out_big);
     // variant 3: levels of at most one ciphertext per SM on the split kernel (four warps per ciphertext: the latency-bound
     // case), up to two per SM on the stream kernel, wide batches on the ring kernel
-    const bool mixed = pbs_variant == 3 || pbs_variant == 5 || pbs_variant == 6 || pbs_variant == 7;      // narrow levels on the split / stream kernels, wide ones on ring (3), solo (5) or quad (6)
+    const bool mixed = pbs_variant == 3 || pbs_variant == 5 || pbs_variant == 6 || pbs_variant == 7 || (pbs_variant == 8 && wide_tx);      // narrow levels on the split / stream kernels, wide ones on ring (3), solo (5) or quad (6)
     if (pbs_variant == 4 || (mixed && use_split && (int)count <= sm_count))
         launch_pbs_split((int)p.acc_bits, pbs_variant == 4 ? bsk_f : bsk_s, in_small, (int)p.lwe_dim, (int)p.pbs_base_log, luts->d,
                          lut_idx_dev, od, out_idx_dev, (int)count, stream);
