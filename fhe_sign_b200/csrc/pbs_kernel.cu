@@ -693,7 +693,7 @@ int pbs_variant_for(int acc_bits) {
     if (e && e[0] == 's') return 2;
     if (e && e[0] == 'q') return 6;
     if (e && e[0] == 'd') return 7;      // "duo": two instruction streams per warp for wide batches, split / stream below      // "quad": four warps per ciphertext at 128 registers for wide batches, split / stream below
-    if (e && e[0] == 'a') return 3;
+    if (e && e[0] == 'a') return acc_bits == 32 ? 3 : 8;
     return acc_bits == 32 ? 3 : 8;      // 8: 64-bit accumulator, ring kernel up to two ciphertexts per SM, pbs_stream_tx_kernel<2, u64> above
 }
 

@@ -1,6 +1,7 @@
 // radix_cuda.cu — device block pool and level execution for the radix layer.
 // A level (radix.h) = upload of a few index arrays, one lincomb launch producing the packed PBS
 // inputs, one keyswitch launch, one PBS launch scattering its outputs into the pool.
+#include <chrono>
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
 #include <stdio.h>
@@ -209,9 +210,14 @@ public:
                 cudaEventDestroy(a); cudaEventDestroy(b);
             }
         } trace_end{e0, e1, eng->stream, reqs.size()};
+        const auto h0 = std::chrono::steady_clock::now();
         ensure_stage_big(reqs.size());
         eng->ensure_scratch(reqs.size());
+        const auto h1 = std::chrono::steady_clock::now();
         const Csr c = upload(reqs, true);
+        const auto h2 = std::chrono::steady_clock::now();
+        if (trace) fprintf(stderr, "   host: ensure buffers %.3f ms, index build + upload call %.3f ms\n",
+                           std::chrono::duration<double, std::milli>(h1 - h0).count(), std::chrono::duration<double, std::milli>(h2 - h1).count());
         cudaEvent_t t1 = nullptr, t2 = nullptr, t3 = nullptr, t4 = nullptr;
         if (trace) { cudaEventCreate(&t1); cudaEventCreate(&t2); cudaEventCreate(&t3); cudaEventCreate(&t4); cudaEventRecord(t1, eng->stream); }
         launch_lincomb(pool, c.row_ptr, c.slot, c.coef, c.cst, delta, stage_big, nullptr, (int)c.count, (int)words, eng->stream);
