@@ -13,7 +13,13 @@
 // 4 700 (75 KB), 2 688 FP64 instructions per warp-step against 3 072 (tangent-form butterflies on every pass).
 // Kernels:
 //   bsk_convert_stream_kernel   standard-domain key -> Fourier domain in the product's consumption order
-//   pbs_stream_kernel<AccT, CTS, NH>
+//   pbs_stream_kernel<AccT, CTS, NH>       the rolled form above: levels of up to two ciphertexts per SM
+//   pbs_stream_tx_kernel<MODE, AccT>       wide batches, four ciphertexts per SM, tensor memory for everything a lane hands to the
+//                                          same lane (partner spectra, accumulator, twist constants).  MODE 2 — the default wide-batch
+//                                          kernel of the library, 91 k PBS/s at 32 bits, 76 k at 64 — is a straight-line step with the
+//                                          two uniform passes specialised (pass32_uniform), whole-complex transposes through a buffer
+//                                          that also holds the by-index accumulator copy, and the int <-> double conversions on the
+//                                          conversion unit; MODE 0 / 1 are the rolled forms kept for comparison (FSC_STREAM_TX).
 //
 // Replaces (concept): tfhe 0.10.0 programmable_bootstrap_lwe_ciphertext (Cargo.lock:482-485), the PBS half of
 // shortint apply_lookup_table behind every operator in src/biguint.rs:110-248.
