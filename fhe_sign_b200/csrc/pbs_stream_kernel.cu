@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_stream_kernel(const cplx* __r
                                                                   int n, int base_log, const uint64_t* __restrict__ luts,
                                                                   const uint32_t* __restrict__ lut_idx, const __grid_constant__ OutDest out_big,
                                                                   const int32_t* __restrict__ out_idx, int count,
-                                                                  const cplx* __restrict__ tabs_g) {
+                                                                  const cplx* __restrict__ tabs_g, int stagger) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pair_t<AccT>* acc_all = reinterpret_cast<pair_t<AccT>*>(smem_raw);
     double* xbuf_all = reinterpret_cast<double*>(smem_raw + (size_t)CTS * 2 * 1024 * sizeof(pair_t<AccT>));
@@ -158,6 +158,11 @@ __global__ void __launch_bounds__(CTS * 64, 1) pbs_stream_kernel(const cplx* __r
     int stage = 0;
     uint32_t phase = 0;
     cplx X[32];
+    if (stagger > 0 && CTS == 4 && ctl >= 2) {      // experiment (FSC_STREAM_STAGGER): here warps w and w + 4 — one sub-partition — belong to
+        const long long t0 = clock64();              // DIFFERENT ciphertexts (ctl = warp >> 1): the second pair of ciphertexts starts late
+        while (clock64() - t0 < (long long)stagger) { }
+        __syncwarp();
+    }
     for (int i = 0; i < n; ++i) {
         if ((i & 31) == 0) a_chunk = (i + lane < n) ? modswitch(ct[i + lane]) : 0;
         const int a = __shfl_sync(0xffffffffu, a_chunk, i & 31);
@@ -770,8 +775,9 @@ static void launch_pbs_stream_t(const void* bsk_f, const uint64_t* in_small, int
                         (size_t)NH * kHalfCplx * sizeof(cplx) + (size_t)kTabCplx * sizeof(cplx) + 2 * NH * sizeof(uint64_t);
     ensure_dynamic_smem(reinterpret_cast<const void*>(&pbs_stream_kernel<AccT, CTS, NH>), smem);      // per device (the opt-in is a per-device attribute)
     const int grid = (count + CTS - 1) / CTS;
+    static const int stagger = [] { const char* e = getenv("FSC_STREAM_STAGGER"); return e ? atoi(e) : 0; }();
     pbs_stream_kernel<AccT, CTS, NH><<<grid, CTS * 64, smem, st>>>(reinterpret_cast<const cplx*>(bsk_f), in_small, n, base_log, luts,
-                                                                          lut_idx, out_big, out_idx, count, stream_tables<AccT>());
+                                                                          lut_idx, out_big, out_idx, count, stream_tables<AccT>(), stagger);
 }
 
 template <typename AccT>
