@@ -41,6 +41,7 @@ struct Engine {
     uint64_t launches = 0;
     // host-buffer entry point: two copy streams so that uploads and downloads overlap the bootstraps of other chunks
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaStream_t lane[2] = {nullptr, nullptr};      // blind rotations of consecutive chunks of fsc_apply_lut_host: the next chunk's CTAs start as SMs free up
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<cudaEvent_t> chunk_events;
     bool host_chunk_explicit = false;    // FSC_HOST_CHUNK_WAVES given: uniform chunks instead of the first-wave | middle | last-wave plan

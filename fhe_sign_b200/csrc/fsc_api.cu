@@ -87,6 +87,7 @@ void Engine::ensure_copy_streams() {
     use();
     FSC_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking));
     FSC_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking));
+    for (auto& l : lane) FSC_CUDA_CHECK(cudaStreamCreateWithFlags(&l, cudaStreamNonBlocking));
     FSC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     FSC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
 }
@@ -119,6 +120,7 @@ Engine::~Engine() {
     if (ev_join) cudaEventDestroy(ev_join);
     if (copy_in) { cudaStreamSynchronize(copy_in); cudaStreamDestroy(copy_in); }
     if (copy_out) { cudaStreamSynchronize(copy_out); cudaStreamDestroy(copy_out); }
+    for (auto& l : lane) if (l) { cudaStreamSynchronize(l); cudaStreamDestroy(l); }
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -590,13 +592,22 @@ fsc_status fsc_apply_lut_host(fsc_ctx* ctx, const uint64_t* in_host, const fsc_l
             for (const auto& pc : plan) {
                 const size_t off = pc.first, c = pc.second;
                 ++k;
-                cudaEvent_t up = e->chunk_event(2 * (k - 1)), done = e->chunk_event(2 * (k - 1) + 1);
+                cudaEvent_t up = e->chunk_event(3 * (k - 1)), done = e->chunk_event(3 * (k - 1) + 1), ksd = e->chunk_event(3 * (k - 1) + 2);
                 FSC_CUDA_CHECK(cudaMemcpyAsync(din + off * words, in_host + off * words, c * words * 8, cudaMemcpyHostToDevice, e->copy_in));
                 FSC_CUDA_CHECK(cudaEventRecord(up, e->copy_in));
                 FSC_CUDA_CHECK(cudaStreamWaitEvent(e->stream, up, 0));
-                e->keyswitch(din + off * words, e->scratch_small + off * nsmall, c);
-                e->pbs(e->scratch_small + off * nsmall, luts, di ? di + off : nullptr, dout + off * words, c);
-                FSC_CUDA_CHECK(cudaEventRecord(done, e->stream));
+                e->keyswitch(din + off * words, e->scratch_small + off * nsmall, c);      // keyswitches stay in order on the context's stream (one digit scratch)
+                FSC_CUDA_CHECK(cudaEventRecord(ksd, e->stream));
+                // the blind rotations of consecutive chunks go to two alternating streams: they touch disjoint ciphertexts, and without
+                // stream order between them the CTAs of chunk k + 1 start as the SMs of chunk k drain instead of after its slowest one
+                cudaStream_t main_stream = e->stream;
+                cudaStream_t ls = e->host_chunk_explicit ? main_stream : e->lane[k & 1];
+                if (ls != main_stream) { FSC_CUDA_CHECK(cudaStreamWaitEvent(ls, ksd, 0)); e->stream = ls; }
+                try {
+                    e->pbs(e->scratch_small + off * nsmall, luts, di ? di + off : nullptr, dout + off * words, c);
+                } catch (...) { e->stream = main_stream; throw; }
+                e->stream = main_stream;
+                FSC_CUDA_CHECK(cudaEventRecord(done, ls));
                 FSC_CUDA_CHECK(cudaStreamWaitEvent(e->copy_out, done, 0));
                 FSC_CUDA_CHECK(cudaMemcpyAsync(out_host + off * words, dout + off * words, c * words * 8, cudaMemcpyDeviceToHost, e->copy_out));
             }
