@@ -161,6 +161,37 @@ def test_apply_lut_host_ragged_and_empty(gpu_ctx, oracle_keys, rng):
         assert (K.decrypt_msgs(out) == np.where(idx == 0, m, 15 - m)).all()
 
 
+def test_apply_lut_host_chunk_plans_agree_bit_for_bit(oracle_keys, rng, monkeypatch):
+    """fsc_apply_lut_host cuts a batch of more than 2.5 kernel waves into first wave | middle | last wave and runs the blind
+    rotations of consecutive chunks on two alternating streams; uniform chunks (FSC_HOST_CHUNK_WAVES) stay on one stream.  The
+    kernels are deterministic per ciphertext, so every plan and the device-resident call must give identical ciphertexts."""
+    import fhe_sign_b200 as fsb
+    from fhe_sign_b200.capi import LWE_BIG
+    K = oracle_keys("toy")
+    count = 4 * 148 * 3 + 400                      # 3.7 waves: three chunks by default, each wide enough for the same (wide-batch) kernel
+    m = rng.integers(0, 16, count).astype(np.uint64)
+    cts = K.encrypt_msgs(m).reshape(count, 2049)
+    idx = rng.integers(0, 2, count).astype(np.uint32)
+    outs = []
+    for waves in (None, "1", "0"):
+        if waves is None:
+            monkeypatch.delenv("FSC_HOST_CHUNK_WAVES", raising=False)
+        else:
+            monkeypatch.setenv("FSC_HOST_CHUNK_WAVES", waves)
+        ctx = fsb.Context(fsb.Params.preset("toy", acc_bits=32))
+        ctx.upload_keys(K.bsk, K.ksk)
+        luts = ctx.luts_from_tables(np.stack([np.arange(16), 15 - np.arange(16)]))
+        outs.append(ctx.apply_lut_host(cts, luts, idx).copy())
+        if waves is None:
+            din, dout = ctx.lwe(LWE_BIG, count).upload(cts), ctx.lwe(LWE_BIG, count)
+            ctx.ks_pbs(din, luts, idx, dout)
+            outs.append(dout.download().copy())
+        ctx.close()
+    assert (K.decrypt_msgs(outs[0]) == np.where(idx == 0, m, 15 - m)).all()
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0])
+
+
 def test_padding_bit_negates(gpu_ctx, oracle_keys):
     """Messages with the padding bit set (m >= 16) come out negated: the negacyclic property every
     radix circuit has to respect."""
